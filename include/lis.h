@@ -1,0 +1,191 @@
+/* lis.h -- C-ABI of the B200-native late-interaction (MaxSim) scoring engine.
+ *
+ * Plain C: pointers, sizes, an opaque index handle.  No torch / C++ types cross this line.
+ * Every pointer documented "device" is a CUDA device pointer owned by the caller; `stream`
+ * is a `cudaStream_t` passed as `void*` (NULL = default stream).  All calls are stream-ordered
+ * and asynchronous with respect to the host unless stated otherwise.
+ *
+ * Return value of every function that returns `int`: 0 on success, a negative LIS_E_* code on
+ * failure; `lis_last_error()` then returns a thread-local human-readable message.
+ *
+ * Reference interfaces each entry point replaces (paths relative to the reference tree):
+ *   - lis_maxsim_scores      <- processor.score_multi_vector(qs, ps)         05_experiment02.py:214
+ *                               (body: colpali-engine 0.3.13, == HF processing_colpali.py:350-364)
+ *   - lis_topk               <- query_scores.topk(top_k)                     05_experiment02.py:219
+ *   - lis_index_*            <- Qdrant multivector collection (MAX_SIM)      01_create_context_qdrant.py:208-222,
+ *                               upsert functions.py:865, query_points functions.py:894-926
+ *   - lis_project_normalize  <- retrieval head inside model(**batch)         functions.py:795,839,888
+ *                               (body: HF modeling_colpali.py:148-155)
+ *   - lis_merge_topk         <- (no reference equivalent; merges per-GPU candidates after the allgather)
+ */
+#ifndef LIS_H_
+#define LIS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIS_ABI_VERSION 1
+
+/* embedding width: VECTOR_SIZE = 128 (01_create_context_qdrant.py:70) */
+#define LIS_DIM 128
+/* query-token rows per tensor-core M tile */
+#define LIS_MTILE 128
+
+enum lis_status {
+  LIS_OK = 0,
+  LIS_E_INVALID = -1,     /* bad argument */
+  LIS_E_CUDA = -2,        /* CUDA runtime / driver error */
+  LIS_E_UNSUPPORTED = -3, /* valid request this build cannot serve (e.g. not an sm_100 device) */
+  LIS_E_NOMEM = -4
+};
+
+enum lis_dtype { LIS_BF16 = 0, LIS_F16 = 1 };
+
+/* Epilogue rounding.  LIS_ROUND_F32: fp32 max and fp32 sum (accuracy mode, checked at 1e-4
+ * against the fp32-widened oracle).  LIS_ROUND_REFERENCE: reproduce what torch does to 16-bit
+ * inputs -- per-token max rounded to the input dtype, summed in fp32, sum rounded to the input
+ * dtype (checked against the reference's bf16 path at 1e-2). */
+enum lis_round_mode { LIS_ROUND_F32 = 0, LIS_ROUND_REFERENCE = 1, LIS_ROUND_DEFER_SUM = 2 };
+
+const char* lis_last_error(void);
+int lis_abi_version(void);
+/* 0 when device `device` can run the kernels (compute capability 10.x), else LIS_E_UNSUPPORTED. */
+int lis_device_supported(int device);
+
+/* ---------------------------------------------------------------------------------------------
+ * Query packing (host-side, pure CPU).
+ *
+ * Queries are ragged lists of token rows, stored back to back ("packed rows": query q owns rows
+ * [sum(len[<q]), sum(len[<=q]))).  The kernel reduces over rows inside one 128-row M tile, so a
+ * query is cut into "segments" wherever it crosses a multiple of 128 rows; the partial sums of a cut
+ * query are added by lis_reduce_segments.  lis_plan_queries computes that segmentation.
+ *   q_lens[nq]                tokens per query (>= 0; a 0-length query owns no segment, score 0)
+ *   seg_query[cap]            out: owning query of each segment
+ *   seg_lo[cap], seg_hi[cap]  out: packed row range [lo, hi) of the segment (inside one M tile)
+ *   mt_seg[mt_cap]            out: mt_seg[t] .. mt_seg[t+1] = segments living in M tile t
+ * Returns the number of segments (>= 0) or a negative status; *n_mtiles receives the tile count.
+ * Call with cap = 0 to size the arrays (returns the segment count, fills *n_mtiles, writes nothing);
+ * mt_cap must be >= *n_mtiles + 1.
+ */
+int64_t lis_plan_queries(const int32_t* q_lens, int64_t nq, int64_t cap, int32_t* seg_query,
+                         int32_t* seg_lo, int32_t* seg_hi, int64_t mt_cap, int32_t* mt_seg,
+                         int64_t* n_mtiles);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1: fused MaxSim.  out[s, p] = sum over rows r of segment s of  max over tokens t of page p
+ * of <q[r,:], tok[t,:]>.   Similarities never leave the SM (TMA -> smem -> tcgen05 -> TMEM ->
+ * registers).
+ *
+ *   q            device [q_rows, 128] packed query rows, dtype; (n_mtiles-1)*128 < q_rows <= n_mtiles*128
+ *                (rows past q_rows inside the last M tile are zero-filled by TMA)
+ *   seg_lo/hi    device int32 [n_seg]        packed-row range of each segment
+ *   mt_seg       device int32 [n_mtiles+1]   segment range of each M tile
+ *   tokens       device [n_rows, 128]        page-token store, row-major, 16-byte aligned
+ *   p_offsets    device int64 [np+1]         page p owns token rows [p_offsets[p], p_offsets[p+1])
+ *                                            (ascending; rows are indices into `tokens`)
+ *   p_clamp      device uint8 [np] or NULL   1 => clamp the per-token max of that page at >= 0.
+ *                                            This is the reference's zero-padding semantics: a page
+ *                                            shorter than the longest page of its 128-page block
+ *                                            sees similarity 0 from the pad rows.
+ *   out          device float [n_seg, ld_out], ld_out >= np
+ */
+int lis_maxsim_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, const int32_t* seg_hi,
+                      const int32_t* mt_seg, int64_t n_seg, int64_t n_mtiles, const void* tokens,
+                      int64_t n_rows, const int64_t* p_offsets, const uint8_t* p_clamp, int64_t np,
+                      int dtype, int round_mode, float* out, int64_t ld_out, void* stream);
+
+/* out[q, p] = sum of seg_scores[s, p] over the segments s of query q, in segment order.
+ * Only needed when some query was cut (n_seg != nq); in that case pass round_mode |
+ * LIS_ROUND_DEFER_SUM to lis_maxsim_scores so the final rounding of LIS_ROUND_REFERENCE happens
+ * here, once, on the complete sum.  seg_first[nq+1] device int32. */
+int lis_reduce_segments(const float* seg_scores, int64_t ld_seg, const int32_t* seg_first, int64_t nq,
+                        int64_t np, int round_mode, int dtype, float* out, int64_t ld_out, void* stream);
+
+/* Tuning / debug knobs (process-wide).  tile_n in {0 (auto), 128, 256}; group in {0 (auto), 1..5};
+ * max_ctas 0 = one per SM.  Used by bench.py sweeps and tests; defaults are what ships. */
+int lis_set_tuning(int tile_n, int group, int max_ctas);
+/* Number of kernels this library launched since load (all entry points). */
+int64_t lis_launch_count(void);
+
+/* Debug: raw similarities of M tile 0 against the first `tile_n` token rows, out[128, tile_n]
+ * (device float), straight from TMEM.  Exercises the exact TMA/UMMA path of lis_maxsim_scores. */
+int lis_debug_sim_tile(const void* q, int64_t q_rows, const void* tokens, int64_t n_rows, int dtype,
+                       int tile_n, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2: per-query top-k over a score matrix, deterministic order (score desc, id asc).
+ *   scores       device float [nq, ld]
+ *   ids          device int64 [np] or NULL (id = id_base + column index)
+ *   out_scores   device float [nq, k]; out_ids device int64 [nq, k]
+ *                (when np < k the tail is filled with -inf / -1)
+ *   workspace    device, lis_topk_workspace_bytes(nq, np, k) bytes
+ * k <= LIS_MAX_K.
+ */
+#define LIS_MAX_K 1024
+int64_t lis_topk_workspace_bytes(int64_t nq, int64_t np, int k);
+int lis_topk(const float* scores, int64_t ld, int64_t nq, int64_t np, const int64_t* ids,
+             int64_t id_base, int k, float* out_scores, int64_t* out_ids, void* workspace,
+             int64_t workspace_bytes, void* stream);
+
+/* Merge candidate lists (e.g. the allgathered per-GPU top-k): cand_scores/cand_ids device
+ * [nq, n_cand]; entries with id < 0 are padding.  Same ordering rule and outputs as lis_topk. */
+int lis_merge_topk(const float* cand_scores, const int64_t* cand_ids, int64_t nq, int64_t n_cand,
+                   int k, float* out_scores, int64_t* out_ids, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3: retrieval head.  out[t,:] = mask[t] * normalize(W h[t,:] + b)   (no epsilon, like the
+ * reference), written as 16-bit rows ready for the page store.
+ *   hidden  device [n_tok, hidden_dim] dtype;  weight device [128, hidden_dim] dtype (row-major,
+ *   i.e. torch Linear.weight);  bias device [128] dtype or NULL;  mask device uint8/ int64-free
+ *   [n_tok] uint8 or NULL;  out device [n_tok,128] dtype.  hidden_dim % 64 == 0.
+ */
+int lis_project_normalize(const void* hidden, int64_t n_tok, int64_t hidden_dim, const void* weight,
+                          const void* bias, const uint8_t* mask, int dtype, void* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Page index: the GPU-resident replacement for the Qdrant multivector collection.
+ * Owns a token store [cap_rows,128], page offsets, page ids and clamp flags on one device.
+ */
+typedef struct lis_index lis_index;
+
+int lis_index_create(lis_index** out, int device, int dtype, int64_t cap_rows, int64_t cap_pages);
+void lis_index_destroy(lis_index* idx);
+/* Append n pages.  `tokens` [sum(lens),128] may be a host or device pointer (cudaMemcpyDefault);
+ * lens host int32 [n]; ids host int64 [n] or NULL (then ids continue from the current count);
+ * clamp host uint8 [n] or NULL (0).  Synchronous with respect to `stream` on return. */
+int lis_index_add(lis_index* idx, const void* tokens, const int32_t* lens, const int64_t* ids,
+                  const uint8_t* clamp, int64_t n, void* stream);
+int64_t lis_index_num_pages(const lis_index* idx);
+int64_t lis_index_num_rows(const lis_index* idx);
+/* Raw views (device pointers) for zero-copy use by the stateless entry points. */
+const void* lis_index_tokens(const lis_index* idx);
+const int64_t* lis_index_offsets(const lis_index* idx);
+const int64_t* lis_index_ids(const lis_index* idx);
+const uint8_t* lis_index_clamp(const lis_index* idx);
+/* Device-side fill for benchmarks: append n pages of unit-norm pseudo-random token rows generated
+ * in place from a counter hash of (seed, global row index) -- a 130 GB shard never exists on the
+ * host.  lens host int32 [n] or NULL (then every page has fixed_len rows).  Ids run from id_base. */
+int lis_index_fill_synthetic(lis_index* idx, int64_t n, const int32_t* lens, int32_t fixed_len,
+                             uint64_t seed, int64_t id_base, void* stream);
+/* Copy token rows [row0, row0+n_rows) of the store to `dst` (host or device), synchronously. */
+int lis_index_read_rows(const lis_index* idx, int64_t row0, int64_t n_rows, void* dst, void* stream);
+/* Stateless version of the generator: fill dst[n_rows,128] (device) with the rows the hash assigns
+ * to global row indices row0 .. row0+n_rows-1. */
+int lis_fill_synthetic_rows(void* dst, int64_t row0, int64_t n_rows, uint64_t seed, int dtype, void* stream);
+/* Search: packed queries (as for lis_maxsim_scores) -> top-k (score, id) per query.
+ * Requires n_seg == nq (no split queries) unless seg_first != NULL (device int32 [nq+1]).
+ * Scratch is owned by the index and grown on demand (outside the timed path after warm-up). */
+int lis_index_search(lis_index* idx, const void* q, int64_t q_rows, const int32_t* seg_lo,
+                     const int32_t* seg_hi, const int32_t* mt_seg, int64_t n_seg, int64_t n_mtiles,
+                     const int32_t* seg_first, int64_t nq, int round_mode, int k, float* out_scores,
+                     int64_t* out_ids, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIS_H_ */

@@ -1,0 +1,20 @@
+"""B200-native late-interaction (MaxSim) scoring engine -- drop-in for the retrieval hot path of
+pkocbek/multi-modal_colpali (``score_multi_vector`` + page-level multivector top-k search).
+
+The directory name contains a hyphen, so import it with
+``importlib.import_module("multi-modal_colpali_b200")`` (or ``import mmcolpali_b200`` from the repo root).
+"""
+from .scoring import score_multi_vector, plan_queries, clamp_flags, maxsim_scores_device, pack_queries, build_page_store
+from .index import LateInteractionIndex, topk_device, merge_topk_device
+from .head import project_normalize
+from .reference_api import (MaxSimClient, PointStruct, QueryResponse, ScoredPoint, ensure_colpali_collection,
+                            retrieve_colpali, score_results, index_for_dataset)
+from .sharded import ShardedIndex, shard_range, balanced_shard_ranges, gather_candidates
+
+__all__ = [
+    "score_multi_vector", "plan_queries", "clamp_flags", "maxsim_scores_device", "pack_queries", "build_page_store",
+    "LateInteractionIndex", "topk_device", "merge_topk_device", "project_normalize",
+    "MaxSimClient", "PointStruct", "QueryResponse", "ScoredPoint", "ensure_colpali_collection",
+    "retrieve_colpali", "score_results", "index_for_dataset",
+    "ShardedIndex", "shard_range", "balanced_shard_ranges", "gather_candidates",
+]

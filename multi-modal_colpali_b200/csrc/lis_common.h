@@ -1,0 +1,47 @@
+// Host-side helpers shared by the C-ABI translation units: thread-local error string,
+// CUDA error mapping, launch counter, driver entry point for tensor-map encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/lis.h"
+
+namespace lis {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct Tuning {
+  int tile_n = 0;
+  int group = 0;
+  int max_ctas = 0;
+};
+extern Tuning g_tuning;
+
+// Encode a 2-D row-major [rows, 128] 16-bit tensor with a (64 col x box_rows) box, 128-byte swizzle.
+int encode_rows_tmap(CUtensorMap* map, const void* base, int64_t rows, int box_rows, int dtype);
+int sm_count(int device);
+
+}  // namespace lis
+
+#define LIS_CUDA_CHECK(expr)                                                                  \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::lis::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return LIS_E_CUDA;                                                                      \
+    }                                                                                         \
+  } while (0)
+
+#define LIS_REQUIRE(cond, ...)          \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::lis::set_error(__VA_ARGS__);    \
+      return LIS_E_INVALID;             \
+    }                                   \
+  } while (0)

@@ -1,0 +1,360 @@
+// C-ABI entry points for the scoring path: query packing, K1 launcher, segment reduction.
+// Interfaces replaced: see include/lis.h.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "lis_common.h"
+#include "maxsim_kernel.cuh"
+
+namespace lis {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+std::atomic<int64_t> g_launches{0};
+Tuning g_tuning;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+int encode_rows_tmap(CUtensorMap* map, const void* base, int64_t rows, int box_rows, int dtype) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return LIS_E_CUDA;
+  }
+  LIS_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor base %p is not 16-byte aligned", base);
+  LIS_REQUIRE(rows > 0 && rows < (int64_t(1) << 31), "row count %lld out of range for one tensor map",
+              (long long)rows);
+  cuuint64_t dims[2] = {(cuuint64_t)kDim, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kDim * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kKHalf, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, dtype == LIS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                   2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld box_rows=%d)", (int)r,
+              (long long)rows, box_rows);
+    return LIS_E_CUDA;
+  }
+  return LIS_OK;
+}
+
+int sm_count(int device) {
+  static int cached[64] = {0};
+  if (device >= 0 && device < 64 && cached[device]) return cached[device];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+  if (device >= 0 && device < 64) cached[device] = n;
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int kSmemBudget = 232448;  // 227 KB opt-in maximum per CTA on sm_100
+constexpr int kSmemTail = 2048;      // barriers + row-max exchange (1264 B used)
+
+template <int NT, int G, bool DBG>
+static int launch_maxsim(const CUtensorMap& tq, const CUtensorMap& tp, const MaxSimArgs& a, int grid,
+                         cudaStream_t st) {
+  const int stage = NT * kDim * 2;
+  int ns = (kSmemBudget - 1024 - kSmemTail - G * kATileBytes) / stage;
+  ns = std::min(ns, 8);
+  if (ns < 1) {
+    set_error("tile_n=%d group=%d does not fit shared memory", NT, G);
+    return LIS_E_INVALID;
+  }
+  const int smem = 1024 + G * kATileBytes + ns * stage + kSmemTail;
+  auto kern = maxsim_kernel<NT, G, DBG>;
+  static bool configured[64] = {false};  // per template instantiation and device
+  int dev = 0;
+  LIS_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    LIS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  kern<<<grid, kNumThreads, smem, st>>>(tq, tp, a, ns);
+  count_launch();
+  LIS_CUDA_CHECK(cudaGetLastError());
+  return LIS_OK;
+}
+
+static int dispatch_maxsim(int nt, int g, const CUtensorMap& tq, const CUtensorMap& tp, const MaxSimArgs& a,
+                           int grid, cudaStream_t st, bool dbg = false) {
+  if (dbg) {
+    if (nt == 256 && g == 1) return launch_maxsim<256, 1, true>(tq, tp, a, grid, st);
+    if (nt == 128 && g == 1) return launch_maxsim<128, 1, true>(tq, tp, a, grid, st);
+  }
+#define LIS_CASE(NT_, G_) \
+  if (nt == NT_ && g == G_) return launch_maxsim<NT_, G_, false>(tq, tp, a, grid, st);
+  LIS_CASE(256, 1) LIS_CASE(256, 2) LIS_CASE(256, 3)
+  LIS_CASE(128, 1) LIS_CASE(128, 2) LIS_CASE(128, 3) LIS_CASE(128, 4) LIS_CASE(128, 5)
+#undef LIS_CASE
+  set_error("unsupported tiling tile_n=%d group=%d", nt, g);
+  return LIS_E_INVALID;
+}
+
+}  // namespace lis
+
+using namespace lis;
+
+extern "C" {
+
+const char* lis_last_error(void) { return g_err; }
+int lis_abi_version(void) { return LIS_ABI_VERSION; }
+int64_t lis_launch_count(void) { return g_launches.load(); }
+
+int lis_device_supported(int device) {
+  int major = 0;
+  LIS_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) {
+    set_error("device %d has compute capability %d.x; this library is built for sm_100a only", device, major);
+    return LIS_E_UNSUPPORTED;
+  }
+  return LIS_OK;
+}
+
+int lis_set_tuning(int tile_n, int group, int max_ctas) {
+  LIS_REQUIRE(tile_n == 0 || tile_n == 128 || tile_n == 256, "tile_n must be 0, 128 or 256");
+  LIS_REQUIRE(group >= 0 && group <= 5, "group must be in 0..5");
+  LIS_REQUIRE(!(tile_n == 256 && group > 3), "tile_n=256 supports group <= 3");
+  LIS_REQUIRE(max_ctas >= 0, "max_ctas must be >= 0");
+  g_tuning.tile_n = tile_n;
+  g_tuning.group = group;
+  g_tuning.max_ctas = max_ctas;
+  return LIS_OK;
+}
+
+int64_t lis_plan_queries(const int32_t* q_lens, int64_t nq, int64_t cap, int32_t* seg_query, int32_t* seg_lo,
+                         int32_t* seg_hi, int64_t mt_cap, int32_t* mt_seg, int64_t* n_mtiles) {
+  if (nq < 0 || (nq > 0 && q_lens == nullptr)) {
+    set_error("lis_plan_queries: bad arguments");
+    return LIS_E_INVALID;
+  }
+  const bool write = cap > 0;
+  int64_t n_seg = 0;
+  int64_t row = 0;  // next packed row
+  for (int64_t q = 0; q < nq; ++q) {
+    int64_t len = q_lens[q];
+    if (len < 0) {
+      set_error("lis_plan_queries: negative length for query %lld", (long long)q);
+      return LIS_E_INVALID;
+    }
+    while (len > 0) {
+      const int64_t room = kMTile - (row % kMTile);  // rows left in the current M tile
+      const int64_t take = std::min<int64_t>(len, room);
+      if (write) {
+        if (n_seg >= cap) {
+          set_error("lis_plan_queries: segment capacity %lld too small", (long long)cap);
+          return LIS_E_INVALID;
+        }
+        seg_query[n_seg] = (int32_t)q;
+        seg_lo[n_seg] = (int32_t)row;
+        seg_hi[n_seg] = (int32_t)(row + take);
+      }
+      ++n_seg;
+      row += take;
+      len -= take;
+    }
+    if (row >= (int64_t(1) << 31) - kMTile) {
+      set_error("lis_plan_queries: too many query rows");
+      return LIS_E_INVALID;
+    }
+  }
+  const int64_t tiles = (row + kMTile - 1) / kMTile;
+  if (n_mtiles) *n_mtiles = tiles;
+  if (write) {
+    if (mt_cap < tiles + 1) {
+      set_error("lis_plan_queries: mt_seg capacity %lld too small (need %lld)", (long long)mt_cap,
+                (long long)(tiles + 1));
+      return LIS_E_INVALID;
+    }
+    int64_t s = 0;
+    for (int64_t t = 0; t <= tiles; ++t) {
+      while (s < n_seg && seg_lo[s] < t * kMTile) ++s;
+      mt_seg[t] = (int32_t)s;
+    }
+  }
+  return n_seg;
+}
+
+}  // extern "C"
+
+namespace lis {
+__global__ void reduce_segments_kernel(const float* __restrict__ seg, int64_t ld_seg,
+                                       const int32_t* __restrict__ seg_first, int64_t np, int round_mode,
+                                       int is_bf16, float* __restrict__ out, int64_t ld_out) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t q = blockIdx.y;
+  if (p >= np) return;
+  const int a = __ldg(seg_first + q), b = __ldg(seg_first + q + 1);
+  float acc = 0.f;
+  for (int s = a; s < b; ++s) acc += __ldg(seg + (int64_t)s * ld_seg + p);
+  if (round_mode & LIS_ROUND_REFERENCE) acc = round_to_input_dtype(acc, is_bf16);
+  out[q * ld_out + p] = acc;
+}
+}  // namespace lis
+
+extern "C" {
+
+int lis_reduce_segments(const float* seg_scores, int64_t ld_seg, const int32_t* seg_first, int64_t nq,
+                        int64_t np, int round_mode, int dtype, float* out, int64_t ld_out, void* stream) {
+  LIS_REQUIRE(seg_scores && seg_first && out, "lis_reduce_segments: null pointer");
+  LIS_REQUIRE(nq > 0 && np > 0 && nq < 65536, "lis_reduce_segments: bad shape nq=%lld np=%lld",
+              (long long)nq, (long long)np);
+  dim3 grid((unsigned)((np + 255) / 256), (unsigned)nq);
+  reduce_segments_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seg_scores, ld_seg, seg_first, np, round_mode,
+                                                                dtype == LIS_BF16, out, ld_out);
+  count_launch();
+  LIS_CUDA_CHECK(cudaGetLastError());
+  return LIS_OK;
+}
+
+static int current_device_sm_count() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  return sm_count(dev);
+}
+
+// Tiling policy.  The op's arithmetic intensity is (query rows) FLOP per page byte, so:
+//   <= 3 M tiles: NT=256 tiles, all M tiles resident (HBM-bound up to ~2 tiles);
+//   more: NT=128 with up to 5 resident M tiles per pass over the page store.
+static void choose_tiling(int64_t n_mtiles, int* nt, int* g) {
+  if (g_tuning.tile_n && g_tuning.group) {
+    *nt = g_tuning.tile_n;
+    *g = g_tuning.group;
+    return;
+  }
+  if (n_mtiles <= 3) {
+    *nt = g_tuning.tile_n ? g_tuning.tile_n : 256;
+    *g = (int)n_mtiles;
+  } else {
+    *nt = g_tuning.tile_n ? g_tuning.tile_n : 128;
+    const int gmax = (*nt == 256) ? 3 : 5;
+    // balance the passes: e.g. 6 tiles -> 3+3 rather than 5+1
+    const int64_t passes = (n_mtiles + gmax - 1) / gmax;
+    *g = (int)((n_mtiles + passes - 1) / passes);
+  }
+  if (g_tuning.group) *g = g_tuning.group;
+  if (*nt == 256 && *g > 3) *g = 3;
+}
+
+int lis_maxsim_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, const int32_t* seg_hi,
+                      const int32_t* mt_seg, int64_t n_seg, int64_t n_mtiles, const void* tokens,
+                      int64_t n_rows, const int64_t* p_offsets, const uint8_t* p_clamp, int64_t np,
+                      int dtype, int round_mode, float* out, int64_t ld_out, void* stream) {
+  LIS_REQUIRE(q && seg_lo && seg_hi && mt_seg && p_offsets && out, "lis_maxsim_scores: null pointer");
+  LIS_REQUIRE(dtype == LIS_BF16 || dtype == LIS_F16, "lis_maxsim_scores: dtype must be bf16 or f16");
+  LIS_REQUIRE(round_mode >= 0 && round_mode <= 3, "bad round_mode");
+  LIS_REQUIRE(n_seg > 0 && n_mtiles > 0 && np > 0, "lis_maxsim_scores: empty problem (n_seg=%lld np=%lld)",
+              (long long)n_seg, (long long)np);
+  LIS_REQUIRE(q_rows > 0 && q_rows > (n_mtiles - 1) * kMTile, "q_rows=%lld inconsistent with n_mtiles=%lld",
+              (long long)q_rows, (long long)n_mtiles);
+  LIS_REQUIRE(ld_out >= np, "ld_out < np");
+  LIS_REQUIRE(n_rows >= 0, "n_rows < 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  int sms = current_device_sm_count();
+  LIS_REQUIRE(sms > 0, "no CUDA device");
+
+  CUtensorMap tq, tp;
+  int rc = encode_rows_tmap(&tq, q, q_rows, kMTile, dtype);
+  if (rc) return rc;
+  int nt, g;
+  choose_tiling(n_mtiles, &nt, &g);
+  // an empty token store still needs a valid map: point it at the query rows (never loaded)
+  rc = n_rows > 0 ? encode_rows_tmap(&tp, tokens, n_rows, nt, dtype) : encode_rows_tmap(&tp, q, q_rows, nt, dtype);
+  if (rc) return rc;
+
+  int grid = sms;
+  if (g_tuning.max_ctas > 0) grid = std::min(grid, g_tuning.max_ctas);
+  grid = (int)std::min<int64_t>(grid, std::max<int64_t>(np, 1));
+
+  for (int64_t mt0 = 0; mt0 < n_mtiles; mt0 += g) {
+    MaxSimArgs a;
+    a.p_offsets = p_offsets;
+    a.p_clamp = p_clamp;
+    a.seg_lo = seg_lo;
+    a.seg_hi = seg_hi;
+    a.mt_seg = mt_seg;
+    a.out = out;
+    a.dbg = nullptr;
+    a.ld_out = ld_out;
+    a.np = np;
+    a.mt0 = (int32_t)mt0;
+    a.n_mt = (int32_t)std::min<int64_t>(g, n_mtiles - mt0);
+    a.round_mode = round_mode;
+    a.is_bf16 = dtype == LIS_BF16;
+    // use the smallest instantiation that holds this pass (the last pass may be short)
+    int gg = a.n_mt;
+    if (nt == 256 && gg > 3) gg = 3;
+    rc = dispatch_maxsim(nt, gg, tq, tp, a, grid, st);
+    if (rc) return rc;
+  }
+  return LIS_OK;
+}
+
+namespace {
+__global__ void fill_iota_offsets(int64_t* off, int32_t* seg_lo, int32_t* seg_hi, int32_t* mt_seg, int64_t rows) {
+  // one page covering all rows; one segment covering M tile 0
+  off[0] = 0; off[1] = rows;
+  seg_lo[0] = 0; seg_hi[0] = 128;
+  mt_seg[0] = 0; mt_seg[1] = 1;
+}
+}  // namespace
+
+int lis_debug_sim_tile(const void* q, int64_t q_rows, const void* tokens, int64_t n_rows, int dtype,
+                       int tile_n, float* out, void* stream) {
+  LIS_REQUIRE(q && tokens && out, "lis_debug_sim_tile: null pointer");
+  LIS_REQUIRE(tile_n == 128 || tile_n == 256, "tile_n must be 128 or 256");
+  LIS_REQUIRE(q_rows > 0 && n_rows > 0, "empty input");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tq, tp;
+  int rc = encode_rows_tmap(&tq, q, q_rows, kMTile, dtype);
+  if (rc) return rc;
+  rc = encode_rows_tmap(&tp, tokens, n_rows, tile_n, dtype);
+  if (rc) return rc;
+  // scratch tables + a dummy score
+  char* scratch = nullptr;
+  LIS_CUDA_CHECK(cudaMalloc(&scratch, 256));
+  int64_t* off = (int64_t*)scratch;
+  int32_t* seg_lo = (int32_t*)(scratch + 32);
+  int32_t* seg_hi = (int32_t*)(scratch + 48);
+  int32_t* mt_seg = (int32_t*)(scratch + 64);
+  float* dummy = (float*)(scratch + 128);
+  fill_iota_offsets<<<1, 1, 0, st>>>(off, seg_lo, seg_hi, mt_seg, std::min<int64_t>(n_rows, tile_n));
+  count_launch();
+  MaxSimArgs a;
+  a.p_offsets = off; a.p_clamp = nullptr; a.seg_lo = seg_lo; a.seg_hi = seg_hi; a.mt_seg = mt_seg;
+  a.out = dummy; a.dbg = out; a.ld_out = 1; a.np = 1; a.mt0 = 0; a.n_mt = 1; a.round_mode = 0;
+  a.is_bf16 = dtype == LIS_BF16;
+  rc = dispatch_maxsim(tile_n, 1, tq, tp, a, 1, st, true);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(scratch);
+  if (rc) return rc;
+  LIS_CUDA_CHECK(e);
+  return LIS_OK;
+}
+
+}  // extern "C"

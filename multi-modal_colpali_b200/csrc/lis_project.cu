@@ -1,0 +1,240 @@
+// K3: fused retrieval head for ingestion.  Restates what the reference runs at the end of
+// model(**batch) (functions.py:795, 839, 888; 05_experiment02.py:211; body HF
+// modeling_colpali.py:148-155):
+//     e = Linear(hidden -> 128)(h);  e = e / ||e||_2 (no epsilon);  e = e * attention_mask
+// as ONE kernel: TMA streams 128-token x 64-feature blocks of h and W, tcgen05 accumulates the
+// [128 tokens x 128 dims] tile in TMEM, and the epilogue (thread = token) adds the bias, takes the
+// row norm, scales, masks and writes the 16-bit row that goes straight into the page store.
+#include <algorithm>
+
+#include "lis_common.h"
+#include "lis_ptx.cuh"
+
+namespace lis {
+
+constexpr int kPTile = 128;                     // tokens per tile (UMMA M)
+constexpr int kPOut = 128;                      // output dims (UMMA N)
+constexpr int kPBlockBytes = kPTile * 128;      // one 64-feature block of A or W: 16 KB
+constexpr int kPStageBytes = 2 * kPBlockBytes;  // A block + W block
+constexpr int kPThreads = 192;
+
+struct ProjectArgs {
+  const void* bias;     // [128] 16-bit or null
+  const uint8_t* mask;  // [n_tok] or null
+  void* out;            // [n_tok, 128] 16-bit
+  int64_t n_tok;
+  int32_t kblocks;      // hidden_dim / 64
+  int32_t is_bf16;
+};
+
+__device__ __forceinline__ float load16(const void* p, int i, int is_bf16) {
+  return is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i])
+                 : __half2float(reinterpret_cast<const __half*>(p)[i]);
+}
+__device__ __forceinline__ uint32_t pack16(float a, float b, int is_bf16) {
+  if (is_bf16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(kPThreads, 1)
+project_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_w,
+               const ProjectArgs args, const int NS) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tail = smem + (size_t)NS * kPStageBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);   // [NS]
+  uint64_t* empty = full + 8;                           // [NS]
+  uint64_t* acc_full = empty + 8;                       // [2]
+  uint64_t* acc_empty = acc_full + 2;                   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sbias = reinterpret_cast<float*>(tmem_slot + 2);  // [128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ntiles = (args.n_tok + kPTile - 1) / kPTile;
+  const int kb = args.kblocks;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_h);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, 4); }
+    fence_barrier_init();
+  }
+  if (threadIdx.x < kPOut) sbias[threadIdx.x] = args.bias ? load16(args.bias, threadIdx.x, args.is_bf16) : 0.f;
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int b = 0; b < kb; ++b, ++it) {
+          const int s = it % NS;
+          mbar_wait(empty + s, ((it / NS) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(full + s, kPStageBytes);
+          uint8_t* dst = smem + (size_t)s * kPStageBytes;
+          tma_load_2d(dst, &tmap_h, full + s, b * 64, (int32_t)(tile * kPTile), kPolicyEvictFirst);
+          tma_load_2d(dst + kPBlockBytes, &tmap_w, full + s, b * 64, 0, kPolicyEvictLast);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(args.is_bf16 ? 1u : 0u, kPTile, kPOut);
+      uint32_t it = 0, use = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++use) {
+        const uint32_t a = use & 1u;
+        mbar_wait(acc_empty + a, ((use >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        for (int b = 0; b < kb; ++b, ++it) {
+          const int s = it % NS;
+          mbar_wait(full + s, (it / NS) & 1u);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * kPStageBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + a * kPOut, make_kmajor_sw128_desc(sa + k * 32),
+                     make_kmajor_sw128_desc(sa + kPBlockBytes + k * 32), idesc, (b | k) ? 1u : 0u);
+          umma_commit(empty + s);
+        }
+        umma_commit(acc_full + a);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    uint32_t use = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++use) {
+      const uint32_t a = use & 1u;
+      mbar_wait(acc_full + a, (use >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * kPOut;
+      const int64_t tok = tile * kPTile + row;
+      float ss = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x = __uint_as_float(v[i]) + sbias[c * 32 + i];
+          ss = fmaf(x, x, ss);
+        }
+      }
+      const float nrm = sqrtf(ss);
+      const float m = (args.mask == nullptr || tok >= args.n_tok) ? 1.f : (__ldg(args.mask + tok) ? 1.f : 0.f);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+        if (tok < args.n_tok) {
+          uint4* dst = reinterpret_cast<uint4*>(static_cast<uint8_t*>(args.out) + tok * 256 + c * 64);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = j * 8 + e * 2;
+              const float x0 = (__uint_as_float(v[i]) + sbias[c * 32 + i]) / nrm * m;
+              const float x1 = (__uint_as_float(v[i + 1]) + sbias[c * 32 + i + 1]) / nrm * m;
+              w[e] = pack16(x0, x1, args.is_bf16);
+            }
+            dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + a);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static int encode_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows, int dtype) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || !p) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return LIS_E_CUDA;
+  }
+  LIS_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor base %p is not 16-byte aligned", base);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<PFN_encodeTiled>(p)(
+      map, dtype == LIS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return LIS_E_CUDA;
+  }
+  return LIS_OK;
+}
+
+}  // namespace lis
+
+using namespace lis;
+
+extern "C" int lis_project_normalize(const void* hidden, int64_t n_tok, int64_t hidden_dim, const void* weight,
+                                     const void* bias, const uint8_t* mask, int dtype, void* out,
+                                     void* stream) {
+  LIS_REQUIRE(hidden && weight && out, "lis_project_normalize: null pointer");
+  LIS_REQUIRE(dtype == LIS_BF16 || dtype == LIS_F16, "dtype must be bf16 or f16");
+  LIS_REQUIRE(n_tok > 0 && n_tok < (int64_t(1) << 31), "n_tok=%lld out of range", (long long)n_tok);
+  LIS_REQUIRE(hidden_dim >= 64 && hidden_dim % 64 == 0 && hidden_dim <= 16384,
+              "hidden_dim=%lld must be a multiple of 64 in [64, 16384]", (long long)hidden_dim);
+  LIS_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "out is not 16-byte aligned");
+  CUtensorMap th, tw;
+  int rc = encode_2d(&th, hidden, n_tok, hidden_dim, kPTile, dtype);
+  if (rc) return rc;
+  rc = encode_2d(&tw, weight, kPOut, hidden_dim, kPOut, dtype);
+  if (rc) return rc;
+  int dev = 0;
+  LIS_CUDA_CHECK(cudaGetDevice(&dev));
+  const int sms = sm_count(dev);
+  LIS_REQUIRE(sms > 0, "no CUDA device");
+  const int ns = 6;
+  const int smem = 1024 + ns * kPStageBytes + 1024;
+  static bool configured[64] = {false};
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    LIS_CUDA_CHECK(cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  ProjectArgs a;
+  a.bias = bias; a.mask = mask; a.out = out; a.n_tok = n_tok;
+  a.kblocks = (int32_t)(hidden_dim / 64);
+  a.is_bf16 = dtype == LIS_BF16;
+  const int64_t ntiles = (n_tok + kPTile - 1) / kPTile;
+  const int grid = (int)std::min<int64_t>(sms, ntiles);
+  project_kernel<<<grid, kPThreads, smem, (cudaStream_t)stream>>>(th, tw, a, ns);
+  count_launch();
+  LIS_CUDA_CHECK(cudaGetLastError());
+  return LIS_OK;
+}

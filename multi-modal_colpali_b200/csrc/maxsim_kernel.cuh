@@ -1,0 +1,325 @@
+// K1: fused late-interaction (MaxSim) scoring kernel for sm_100a.
+//
+//   out[s, p] = sum_{r in segment s} max_{t in page p} <q[r,:], tok[t,:]>
+//
+// restating the arithmetic of score_multi_vector (reference call site 05_experiment02.py:214;
+// body colpali-engine 0.3.13 == HF processing_colpali.py:360: einsum("bnd,csd->bcns").max(3).sum(2))
+// without ever materialising the [B,C,N,S] similarity tensor.
+//
+// Layout / roles (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: query M tiles once (A operand, resident), then the CTA's slice of the
+//               page-token store as flat NT-row tiles through an NS-stage mbarrier ring (B operand).
+//   warp 1      tcgen05.mma issuer (one lane).  For every B tile: G MMAs (one per resident M tile),
+//               each 128 x NT x 128 (8 k-steps of 16), accumulators in a ring of 512/NT TMEM buffers.
+//   warps 2..5  epilogue: tcgen05.ld the accumulator (thread = query-token row), running per-page
+//               row max in registers (FMNMX3), page boundaries handled by column masks, then a
+//               segmented sum over the rows of each query through shared memory -> one fp32 per
+//               (query segment, page) to HBM.
+//
+// The page-token store is tiled FLAT (tiles ignore page boundaries); a CTA owns a contiguous range of
+// whole pages, so no partial maxima ever cross CTAs and ragged pages cost no padding reads.
+#pragma once
+#include "lis_ptx.cuh"
+
+namespace lis {
+
+constexpr int kDim = 128;        // embedding width (VECTOR_SIZE, 01_create_context_qdrant.py:70)
+constexpr int kMTile = 128;      // query rows per UMMA
+constexpr int kKHalf = 64;       // elements per 128-byte swizzle atom
+constexpr int kATileBytes = kMTile * kDim * 2;  // 32 KB
+constexpr int kNumThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kTmemCols = 512;
+
+struct MaxSimArgs {
+  const int64_t* p_offsets;  // [np+1]
+  const uint8_t* p_clamp;    // [np] or null
+  const int32_t* seg_lo;     // [n_seg]
+  const int32_t* seg_hi;     // [n_seg]
+  const int32_t* mt_seg;     // [n_mtiles_total+1]
+  float* out;                // [n_seg, ld_out]
+  float* dbg;                // debug: raw sims of (tile 0 of CTA 0), [G*128, NT]; normally null
+  int64_t ld_out;
+  int64_t np;
+  int32_t mt0;        // first M tile of this launch
+  int32_t n_mt;       // M tiles in this launch (1..G)
+  int32_t round_mode; // lis_round_mode bits
+  int32_t is_bf16;    // 1 = bf16, 0 = fp16
+};
+
+__device__ __forceinline__ float round_to_input_dtype(float x, int is_bf16) {
+  return is_bf16 ? __bfloat162float(__float2bfloat16_rn(x)) : __half2float(__float2half_rn(x));
+}
+
+__device__ __forceinline__ float max32(const uint32_t (&v)[32], float m) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) m = fmax3(m, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+  return m;
+}
+__device__ __forceinline__ float max32_masked(const uint32_t (&v)[32], float m, int lo, int hi) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float x = (i >= lo && i < hi) ? __uint_as_float(v[i]) : -INFINITY;
+    m = fmaxf(m, x);
+  }
+  return m;
+}
+
+// first index i in [0, n] with off[i] >= target (off ascending, n+1 entries)
+__device__ __forceinline__ int64_t lower_bound_off(const int64_t* off, int64_t n, int64_t target) {
+  int64_t lo = 0, hi = n;  // answer in [lo, hi]; off[n] >= any target we pass
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(off + mid) >= target) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+template <int NT, int G, bool DBG>
+__global__ void __launch_bounds__(kNumThreads, 1)
+maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_p,
+              const MaxSimArgs args, const int NS) {
+  static_assert(NT == 128 || NT == 256, "tile_n");
+  constexpr int NACC = kTmemCols / NT;
+  constexpr int kBStageBytes = NT * kDim * 2;
+  constexpr int kBHalfBytes = NT * 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                               // [G][2][128 rows x 128 B]
+  uint8_t* smem_b = smem + G * kATileBytes;             // [NS][2][NT rows x 128 B]
+  uint8_t* tail = smem_b + (size_t)NS * kBStageBytes;
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(tail);      // 1
+  uint64_t* b_full = q_full + 1;                             // [NS]
+  uint64_t* b_empty = b_full + 8;                            // [NS]
+  uint64_t* acc_full = b_empty + 8;                          // [NACC]
+  uint64_t* acc_empty = acc_full + 4;                        // [NACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
+  int64_t* range = reinterpret_cast<int64_t*>(tmem_slot + 2);  // [0]=page begin [1]=page end [2]=row0
+  float* srm = reinterpret_cast<float*>(range + 4);            // [2][128] row-max exchange
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_p);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < NS; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+    for (int a = 0; a < NACC; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, 4); }
+    fence_barrier_init();
+    // This CTA's contiguous range of whole pages, balanced by token rows.
+    const int64_t np = args.np;
+    const int64_t base = __ldg(args.p_offsets);
+    const int64_t total = __ldg(args.p_offsets + np) - base;
+    const int64_t per = (total + gridDim.x - 1) / gridDim.x;
+    int64_t pa = np, pb = np;
+    if (per > 0 && (int64_t)blockIdx.x * per < total) {
+      pa = lower_bound_off(args.p_offsets, np, base + (int64_t)blockIdx.x * per);
+      pb = (blockIdx.x + 1 == gridDim.x || (int64_t)(blockIdx.x + 1) * per >= total)
+               ? np
+               : lower_bound_off(args.p_offsets, np, base + (int64_t)(blockIdx.x + 1) * per);
+    } else if (total == 0 && blockIdx.x == 0) {
+      pa = 0; pb = np;  // only empty pages: CTA 0 emits them
+    }
+    range[0] = pa;
+    range[1] = pb;
+    range[2] = (pa < np) ? __ldg(args.p_offsets + pa) : 0;
+    range[3] = (pa < pb) ? __ldg(args.p_offsets + pb) : range[2];
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t pa = range[0], pb = range[1];
+  const int64_t row0 = range[2];
+  const int64_t rows = range[3] - row0;
+  const int ntiles = (int)((rows + NT - 1) / NT);
+  const int n_mt = args.n_mt;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0 && pa < pb) {
+      if (ntiles > 0) {
+        mbar_arrive_expect_tx(q_full, (uint32_t)n_mt * kATileBytes);
+        for (int g = 0; g < n_mt; ++g)
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d(smem_a + g * kATileBytes + h * (kMTile * 128), &tmap_q, q_full, h * kKHalf,
+                        (args.mt0 + g) * kMTile, kPolicyEvictLast);
+      }
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t % NS;
+        const uint32_t ph = (uint32_t)(t / NS) & 1u;
+        mbar_wait(b_empty + s, ph ^ 1u);
+        mbar_arrive_expect_tx(b_full + s, kBStageBytes);
+        uint8_t* dst = smem_b + (size_t)s * kBStageBytes;
+        const int32_t r = (int32_t)(row0 + (int64_t)t * NT);
+        tma_load_2d(dst, &tmap_p, b_full + s, 0, r, kPolicyEvictFirst);
+        tma_load_2d(dst + kBHalfBytes, &tmap_p, b_full + s, kKHalf, r, kPolicyEvictFirst);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && pa < pb && ntiles > 0) {
+      const uint32_t idesc = make_idesc_f16(args.is_bf16 ? 1u : 0u, kMTile, NT);
+      const uint32_t a_base = smem_u32(smem_a);
+      const uint32_t b_base = smem_u32(smem_b);
+      mbar_wait(q_full, 0);
+      uint32_t use = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t % NS;
+        mbar_wait(b_full + s, (uint32_t)(t / NS) & 1u);
+        tc_fence_after();
+        for (int g = 0; g < n_mt; ++g, ++use) {
+          const uint32_t a = use % NACC;
+          mbar_wait(acc_empty + a, ((use / NACC) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + a * NT;
+#pragma unroll
+          for (int k = 0; k < kDim / 16; ++k) {
+            const uint32_t koff = (uint32_t)(k >> 2) * (kMTile * 128) + (uint32_t)(k & 3) * 32;
+            const uint32_t koff_b = (uint32_t)(k >> 2) * kBHalfBytes + (uint32_t)(k & 3) * 32;
+            const uint64_t adesc = make_kmajor_sw128_desc(a_base + g * kATileBytes + koff);
+            const uint64_t bdesc = make_kmajor_sw128_desc(b_base + s * kBStageBytes + koff_b);
+            umma_f16(d_tmem, adesc, bdesc, idesc, k > 0 ? 1u : 0u);
+          }
+          umma_commit(acc_full + a);
+        }
+        umma_commit(b_empty + s);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;      // query-token row inside the M tile
+    const int etid = row;                     // 0..127, also the "segment worker" index
+    const int is_bf16 = args.is_bf16;
+    const bool round_ref = (args.round_mode & 1) != 0;            // round the per-token max
+    const bool round_sum = round_ref && (args.round_mode & 2) == 0;  // ... and the sum, unless deferred
+
+    // segment handled by this thread in each resident M tile
+    int seg_id[G], s_lo[G], s_hi[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      seg_id[g] = -1; s_lo[g] = 0; s_hi[g] = 0;
+      if (g < n_mt) {
+        const int first = __ldg(args.mt_seg + args.mt0 + g);
+        const int last = __ldg(args.mt_seg + args.mt0 + g + 1);
+        if (first + etid < last) {
+          seg_id[g] = first + etid;
+          s_lo[g] = __ldg(args.seg_lo + seg_id[g]) - (args.mt0 + g) * kMTile;
+          s_hi[g] = __ldg(args.seg_hi + seg_id[g]) - (args.mt0 + g) * kMTile;
+        }
+      }
+    }
+
+    float rm[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) rm[g] = -INFINITY;
+    int par = 0;
+
+    // Emit one finished page for M tile g: clamp / round the row max, exchange through smem,
+    // then the segment workers sum their rows in ascending row order (deterministic).
+    auto finish_page = [&](int g, int64_t p, float v) {
+      if (args.p_clamp != nullptr && __ldg(args.p_clamp + p)) v = fmaxf(v, 0.f);
+      if (round_ref) v = round_to_input_dtype(v, is_bf16);
+      srm[par * kMTile + row] = v;
+      named_bar_sync(1, kEpiThreads);
+#pragma unroll
+      for (int gg = 0; gg < G; ++gg) {
+        if (gg == g && seg_id[gg] >= 0) {
+          float acc = 0.f;
+          for (int r = s_lo[gg]; r < s_hi[gg]; ++r) acc += srm[par * kMTile + r];
+          if (round_sum) acc = round_to_input_dtype(acc, is_bf16);
+          args.out[(int64_t)seg_id[gg] * args.ld_out + p] = acc;
+        }
+      }
+      par ^= 1;
+    };
+
+    if (pa < pb) {
+      // leading empty pages (and the all-empty corner case) produce -inf / clamped rows
+      int64_t p = pa;                                   // current page
+      int64_t pend = __ldg(args.p_offsets + p + 1);     // its end row (global)
+      uint32_t use = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int64_t trow = row0 + (int64_t)t * NT;    // global row of column 0
+        int64_t p_next = p, pend_next = pend;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (g < n_mt) {
+            const uint32_t a = use % NACC;
+            mbar_wait(acc_full + a, (use / NACC) & 1u);
+            tc_fence_after();
+            ++use;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * NT;
+            int64_t pp = p, ppend = pend;   // rewind the page cursor for every M tile
+            float m = rm[g];
+            bool live = pp < pb;
+#pragma unroll 1
+            for (int c = 0; c < NT / 32; ++c) {
+              uint32_t v[32];
+              tmem_ld32(taddr + c * 32, v);
+              tmem_ld_wait();
+              if (DBG) {
+                if (blockIdx.x == 0 && t == 0 && args.dbg != nullptr) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    args.dbg[(int64_t)(g * kMTile + row) * NT + c * 32 + i] = __uint_as_float(v[i]);
+                }
+              }
+              if (!live) continue;
+              const int64_t cb = trow + c * 32;         // global row of this chunk's column 0
+              if (ppend - cb > 32) {
+                m = max32(v, m);
+              } else {
+                int lo = 0;
+                while (true) {
+                  const int64_t rel = ppend - cb;
+                  const int hi = rel < 32 ? (int)rel : 32;
+                  m = max32_masked(v, m, lo, hi);
+                  if (rel > 32) break;
+                  finish_page(g, pp, m);
+                  m = -INFINITY;
+                  ++pp;
+                  if (pp >= pb) { live = false; break; }
+                  ppend = __ldg(args.p_offsets + pp + 1);
+                  lo = hi;
+                  if (lo >= 32) break;
+                }
+              }
+            }
+            rm[g] = m;
+            p_next = pp; pend_next = ppend;
+            // release the accumulator buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + a);
+          }
+        }
+        p = p_next; pend = pend_next;
+      }
+      // pages not closed by any tile: trailing empty pages (or ntiles == 0)
+      while (p < pb) {
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          if (g < n_mt) { finish_page(g, p, rm[g]); rm[g] = -INFINITY; }
+        ++p;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace lis

@@ -1,0 +1,220 @@
+"""GPU-resident page index + top-k search: the in-process replacement for the reference's two
+search routes --
+
+* ``score_results`` (05_experiment02.py:200-236): stack the whole corpus, ``score_multi_vector``,
+  ``topk`` per query, gather page metadata;
+* ``retrieve_colpali`` (functions.py:884-929): Qdrant ``query_points`` on a multivector MAX_SIM
+  collection (schema 01_create_context_qdrant.py:208-222).
+
+The index object is a thin handle on the C-side ``lis_index`` (tokens / offsets / ids live in HBM
+and are owned by the library); payloads stay in a host-side dict keyed by page id.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .scoring import (TensorOrList, _DTYPES, _ROUND, _as_list, _check_rows, _stream, clamp_flags,
+                      pack_queries, resolve_device)
+
+_TORCH_DTYPE = {N.LIS_BF16: torch.bfloat16, N.LIS_F16: torch.float16}
+
+
+class LateInteractionIndex:
+    """Ragged multi-vector page store on one GPU with fused MaxSim + top-k search.
+
+    ``capacity_rows`` / ``capacity_pages`` are fixed at construction (HBM is sized once; a 180 GB
+    B200 holds ~680 M token rows = 660 k ColPali pages of 1030 tokens)."""
+
+    def __init__(self, capacity_rows: int, capacity_pages: int, dtype: torch.dtype = torch.bfloat16,
+                 device: Union[str, torch.device, None] = None):
+        if dtype not in _DTYPES:
+            raise NotImplementedError(f"index dtype {dtype}: bfloat16 or float16")
+        self.device = resolve_device(device)
+        self.dtype = dtype
+        self._lib = N.load()
+        self._h = C.c_void_p()
+        N.check(self._lib.lis_index_create(C.byref(self._h), self.device.index, _DTYPES[dtype],
+                                           int(capacity_rows), int(capacity_pages)))
+        self.payloads: Dict[int, Any] = {}
+
+    # -- lifetime ---------------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.lis_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        return int(self._lib.lis_index_num_pages(self._h))
+
+    @property
+    def num_rows(self) -> int:
+        return int(self._lib.lis_index_num_rows(self._h))
+
+    # -- ingestion --------------------------------------------------------------------------------
+    def add(self, pages: TensorOrList, ids: Optional[Sequence[int]] = None,
+            payloads: Optional[Sequence[Any]] = None, zero_pad_block: Optional[int] = None) -> np.ndarray:
+        """Append pages (list of ``[n_tok,128]`` tensors or one ``[n, S, 128]`` tensor, host or device).
+
+        ``zero_pad_block``: when set, pages shorter than the longest page of their block of that many
+        consecutive pages get the reference's zero-padding semantics (per-token max clamped at 0), as
+        ``score_multi_vector`` does with its 128-page batches.  Returns the assigned ids."""
+        pl = _as_list(pages)
+        if not pl:
+            return np.zeros(0, np.int64)
+        for t in pl:
+            _check_rows(t, "page")
+        lens = np.asarray([int(t.shape[0]) for t in pl], dtype=np.int32)
+        n = len(pl)
+        first = len(self)
+        id_arr = np.arange(first, first + n, dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
+        if id_arr.shape != (n,):
+            raise ValueError("ids must have one entry per page")
+        clamp = clamp_flags(lens, zero_pad_block) if zero_pad_block else None
+        if isinstance(pages, torch.Tensor):
+            flat = pages.reshape(-1, N.DIM)
+        else:
+            flat = torch.cat(pl, dim=0)
+        flat = flat.to(self.dtype).contiguous()
+        with torch.cuda.device(self.device):
+            N.check(self._lib.lis_index_add(self._h, flat.data_ptr(), lens.ctypes.data, id_arr.ctypes.data,
+                                            None if clamp is None else clamp.ctypes.data, n,
+                                            _stream(self.device)))
+        if payloads is not None:
+            if len(payloads) != n:
+                raise ValueError("payloads must have one entry per page")
+            for i, pay in zip(id_arr.tolist(), payloads):
+                self.payloads[i] = pay
+        return id_arr
+
+    def fill_synthetic(self, n_pages: int, page_len: Union[int, Sequence[int]], seed: int, id_base: int = 0) -> None:
+        """Append unit-norm pseudo-random pages generated on the device (benchmarks; see lis.h)."""
+        lens = None
+        fixed = 0
+        if isinstance(page_len, (int, np.integer)):
+            fixed = int(page_len)
+        else:
+            lens = np.ascontiguousarray(page_len, dtype=np.int32)
+            if lens.shape != (n_pages,):
+                raise ValueError("page_len must be an int or one length per page")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.lis_index_fill_synthetic(self._h, int(n_pages), None if lens is None else lens.ctypes.data,
+                                                       fixed, int(seed), int(id_base), _stream(self.device)))
+
+    def read_rows(self, row0: int, n_rows: int) -> torch.Tensor:
+        """Copy token rows back to the host (tests / debugging)."""
+        out = torch.empty((n_rows, N.DIM), dtype=self.dtype)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.lis_index_read_rows(self._h, int(row0), int(n_rows), out.data_ptr(), _stream(self.device)))
+        return out
+
+    # -- search -----------------------------------------------------------------------------------
+    def search_device(self, qs: TensorOrList, k: int, round_mode: str = "f32") -> Tuple[torch.Tensor, torch.Tensor]:
+        """MaxSim + top-k entirely on the device; returns device tensors (scores fp32 [nq,k], ids int64 [nq,k])."""
+        if len(qs) == 0:
+            raise ValueError("No queries provided")
+        if len(self) == 0:
+            raise ValueError("No passages provided")
+        if round_mode not in _ROUND:
+            raise ValueError(f"round_mode must be one of {sorted(_ROUND)}")
+        with torch.cuda.device(self.device):
+            pq = pack_queries(qs, self.device, self.dtype)
+            plan = pq.plan
+            seg_lo, seg_hi, mt_seg, seg_first = pq.table_ptrs()
+            out_s = torch.empty((plan.nq, k), dtype=torch.float32, device=self.device)
+            out_i = torch.empty((plan.nq, k), dtype=torch.int64, device=self.device)
+            N.check(self._lib.lis_index_search(self._h, pq.rows.data_ptr(), pq.rows.shape[0], seg_lo, seg_hi, mt_seg,
+                                               plan.n_seg, plan.n_mtiles, seg_first, plan.nq, _ROUND[round_mode],
+                                               int(k), out_s.data_ptr(), out_i.data_ptr(), _stream(self.device)))
+        return out_s, out_i
+
+    def search(self, qs: TensorOrList, k: int, round_mode: str = "f32") -> Tuple[torch.Tensor, torch.Tensor]:
+        """Host-facing search: (scores fp32 [nq,k], page ids int64 [nq,k]) on the CPU, best first,
+        ties broken by ascending id; slots beyond the corpus size hold (-inf, -1)."""
+        s, i = self.search_device(qs, k, round_mode)
+        return s.cpu(), i.cpu()
+
+    def scores(self, qs: TensorOrList, round_mode: str = "f32") -> torch.Tensor:
+        """Full device fp32 ``[nq, n_pages]`` score matrix against the resident corpus."""
+        from .scoring import PageStore, maxsim_scores_device
+
+        with torch.cuda.device(self.device):
+            pq = pack_queries(qs, self.device, self.dtype)
+            store = self._as_store()
+            return maxsim_scores_device(pq, store, round_mode)
+
+    def _as_store(self):
+        from .scoring import PageStore
+
+        n, rows = len(self), self.num_rows
+        tok = _wrap_device(self._lib.lis_index_tokens(self._h), (rows, N.DIM), self.dtype, self.device)
+        off = _wrap_device(self._lib.lis_index_offsets(self._h), (n + 1,), torch.int64, self.device)
+        cl = _wrap_device(self._lib.lis_index_clamp(self._h), (n,), torch.uint8, self.device)
+        return PageStore(tok, off, cl, n)
+
+
+class _CudaArrayView:
+    """Minimal ``__cuda_array_interface__`` carrier so torch can alias library-owned HBM."""
+
+    def __init__(self, ptr: int, shape: Tuple[int, ...], typestr: str):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def _wrap_device(ptr: int, shape: Tuple[int, ...], dtype: torch.dtype, device: torch.device) -> torch.Tensor:
+    if dtype in (torch.bfloat16, torch.float16):
+        t = torch.as_tensor(_CudaArrayView(ptr, shape, "<i2"), device=device)
+        return t.view(dtype)
+    typestr = {torch.int64: "<i8", torch.uint8: "|u1", torch.float32: "<f4"}[dtype]
+    return torch.as_tensor(_CudaArrayView(ptr, shape, typestr), device=device)
+
+
+def topk_device(scores: torch.Tensor, k: int, ids: Optional[torch.Tensor] = None, id_base: int = 0
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K2 on a device fp32 ``[nq, np]`` matrix (replaces ``query_scores.topk(top_k)``,
+    05_experiment02.py:219).  ``ids`` int64 ``[np]`` maps columns to page ids; entries < 0 are
+    excluded (this is how payload filters are applied).  Order: score desc, id asc."""
+    lib = N.load()
+    if scores.dim() != 2 or scores.dtype != torch.float32 or not scores.is_cuda:
+        raise ValueError("scores must be a CUDA float32 [nq, np] tensor")
+    if scores.stride(1) != 1:
+        scores = scores.contiguous()
+    nq, npg = scores.shape
+    dev = scores.device
+    with torch.cuda.device(dev):
+        ws_bytes = int(lib.lis_topk_workspace_bytes(nq, npg, int(k)))
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        out_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        N.check(lib.lis_topk(scores.data_ptr(), scores.stride(0), nq, npg, None if ids is None else ids.data_ptr(),
+                             int(id_base), int(k), out_s.data_ptr(), out_i.data_ptr(), ws.data_ptr(), ws.numel(),
+                             _stream(dev)))
+    return out_s, out_i
+
+
+def merge_topk_device(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge candidate lists ``[nq, n_cand]`` (e.g. allgathered per-GPU top-k) into the global top-k."""
+    lib = N.load()
+    if cand_scores.shape != cand_ids.shape or cand_scores.dim() != 2:
+        raise ValueError("candidate scores / ids must both be [nq, n_cand]")
+    cand_scores = cand_scores.contiguous()
+    cand_ids = cand_ids.contiguous()
+    nq, nc = cand_scores.shape
+    dev = cand_scores.device
+    with torch.cuda.device(dev):
+        ws_bytes = int(lib.lis_topk_workspace_bytes(nq, nc, int(k)))
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        out_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        N.check(lib.lis_merge_topk(cand_scores.data_ptr(), cand_ids.data_ptr(), nq, nc, int(k), out_s.data_ptr(),
+                                   out_i.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
+    return out_s, out_i

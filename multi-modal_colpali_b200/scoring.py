@@ -1,0 +1,285 @@
+"""Drop-in for ``processor.score_multi_vector(qs, ps)`` (reference call site
+``05_experiment02.py:214``; body in colpali-engine 0.3.13, arithmetic identical to HF
+``processing_colpali.py:350-364``), backed by the fused sm_100a kernel.
+
+PyTorch is used for device memory and streams only; all arithmetic happens in ``liblis.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from functools import lru_cache
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+TensorOrList = Union[torch.Tensor, Sequence[torch.Tensor]]
+
+_DTYPES = {torch.bfloat16: N.LIS_BF16, torch.float16: N.LIS_F16}
+_ROUND = {"f32": N.ROUND_F32, "reference": N.ROUND_REFERENCE}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def resolve_device(device: Union[str, torch.device, None]) -> torch.device:
+    """The reference picks cuda -> mps -> cpu automatically; this engine is CUDA-only by design."""
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("multi-modal_colpali_b200 needs an sm_100 (B200) GPU; there is no CPU fallback")
+        return torch.device("cuda", torch.cuda.current_device())
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"device {dev} is not supported: the scoring engine is sm_100a CUDA only")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+# ------------------------------------------------------------------------------------------------
+# Query packing (host logic; runs without a GPU)
+# ------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class QueryPlan:
+    """Segmentation of back-to-back query rows at 128-row M-tile boundaries (``lis_plan_queries``)."""
+    nq: int
+    n_rows: int             # total query-token rows
+    n_seg: int
+    n_mtiles: int
+    seg_query: np.ndarray   # int32 [n_seg]
+    seg_lo: np.ndarray      # int32 [n_seg]
+    seg_hi: np.ndarray      # int32 [n_seg]
+    mt_seg: np.ndarray      # int32 [n_mtiles+1]
+    seg_first: np.ndarray   # int32 [nq+1]  segments of query q = seg_first[q]..seg_first[q+1]
+
+    @property
+    def direct(self) -> bool:
+        """True when no query was cut: K1's output rows are the per-query scores."""
+        return self.n_seg == self.nq
+
+
+def plan_queries(q_lens: Sequence[int]) -> QueryPlan:
+    return _plan_cached(tuple(int(x) for x in q_lens))
+
+
+@lru_cache(maxsize=256)
+def _plan_cached(q_lens: Tuple[int, ...]) -> QueryPlan:
+    lib = N.load()
+    nq = len(q_lens)
+    lens = np.asarray(q_lens, dtype=np.int32)
+    n_mt = C.c_int64(0)
+    n_seg = lib.lis_plan_queries(lens.ctypes.data, nq, 0, None, None, None, 0, None, C.byref(n_mt))
+    N.check(n_seg)
+    cap = max(int(n_seg), 1)
+    seg_query = np.zeros(cap, np.int32)
+    seg_lo = np.zeros(cap, np.int32)
+    seg_hi = np.zeros(cap, np.int32)
+    mt_seg = np.zeros(int(n_mt.value) + 1, np.int32)
+    got = lib.lis_plan_queries(lens.ctypes.data, nq, cap, seg_query.ctypes.data, seg_lo.ctypes.data,
+                               seg_hi.ctypes.data, len(mt_seg), mt_seg.ctypes.data, C.byref(n_mt))
+    N.check(got)
+    n_seg = int(got)
+    seg_query, seg_lo, seg_hi = seg_query[:n_seg], seg_lo[:n_seg], seg_hi[:n_seg]
+    seg_first = np.searchsorted(seg_query, np.arange(nq + 1), side="left").astype(np.int32)
+    return QueryPlan(nq, int(lens.sum()), n_seg, int(n_mt.value), seg_query, seg_lo, seg_hi, mt_seg, seg_first)
+
+
+def clamp_flags(p_lens: Sequence[int], batch_size: int = 128) -> np.ndarray:
+    """uint8 [np]: 1 where the reference's zero padding is visible to the page, i.e. the page is
+    shorter than the longest page of its ``batch_size`` block (``pad_sequence(..., padding_value=0)``
+    at HF processing_colpali.py:355-357 adds similarity-0 rows that take part in the max)."""
+    lens = np.asarray(p_lens, dtype=np.int64)
+    out = np.zeros(len(lens), np.uint8)
+    for j in range(0, len(lens), batch_size):
+        blk = lens[j:j + batch_size]
+        out[j:j + batch_size] = (blk < blk.max()).astype(np.uint8)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Device-side preparation
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class PackedQueries:
+    plan: QueryPlan
+    rows: torch.Tensor      # [n_rows, 128] 16-bit, device: the queries' token rows back to back
+    tables: torch.Tensor    # int32 device: seg_lo | seg_hi | mt_seg | seg_first
+    dtype: torch.dtype
+
+    def table_ptrs(self) -> Tuple[int, int, int, int]:
+        p, ns, nm = self.tables.data_ptr(), self.plan.n_seg, self.plan.n_mtiles
+        return p, p + 4 * ns, p + 8 * ns, p + 8 * ns + 4 * (nm + 1)
+
+
+def _as_list(x: TensorOrList) -> List[torch.Tensor]:
+    if isinstance(x, torch.Tensor):
+        if x.dim() != 3:
+            raise ValueError(f"expected a [n, tokens, {N.DIM}] tensor, got shape {tuple(x.shape)}")
+        return list(torch.unbind(x, dim=0))
+    return list(x)
+
+
+def _check_rows(t: torch.Tensor, what: str) -> None:
+    if t.dim() != 2 or t.shape[1] != N.DIM:
+        raise ValueError(f"{what}: expected [tokens, {N.DIM}], got {tuple(t.shape)}")
+
+
+def _common_dtype(tensors: Sequence[torch.Tensor], what: str) -> torch.dtype:
+    dt = tensors[0].dtype
+    for t in tensors:
+        if t.dtype != dt:
+            raise ValueError(f"{what} mix dtypes {dt} and {t.dtype}")
+    return dt
+
+
+def pack_queries(qs: TensorOrList, device: torch.device, dtype: Optional[torch.dtype] = None) -> PackedQueries:
+    """Move queries to ``device`` as one [rows, 128] matrix plus their segment tables."""
+    if isinstance(qs, torch.Tensor) and qs.dim() == 3:
+        nq, n_tok, d = qs.shape
+        if d != N.DIM:
+            raise ValueError(f"queries: embedding width {d} != {N.DIM}")
+        lens = (n_tok,) * nq
+        flat = qs.reshape(nq * n_tok, d)
+    else:
+        ql = _as_list(qs)
+        for t in ql:
+            _check_rows(t, "query")
+        if ql:
+            _common_dtype(ql, "queries")
+        lens = tuple(int(t.shape[0]) for t in ql)
+        if ql and all(t.device.type == "cpu" for t in ql):
+            flat = torch.cat(ql, dim=0)  # one host gather, then a single H2D copy
+        else:
+            flat = torch.cat([t.to(device, non_blocking=True) for t in ql], dim=0) if ql else None
+    plan = plan_queries(lens)
+    if plan.n_seg == 0:
+        raise ValueError("No queries provided")
+    dt = dtype or flat.dtype
+    if dt not in _DTYPES:
+        raise NotImplementedError(f"query dtype {dt}: the tensor-core path takes bfloat16 or float16 embeddings")
+    rows = flat.to(device=device, dtype=dt, non_blocking=True).contiguous()
+    if rows.data_ptr() % 16:
+        rows = rows.clone()
+    return PackedQueries(plan, rows, _device_tables(plan, device), dt)
+
+
+_TABLE_CACHE: dict = {}
+
+
+def _device_tables(plan: QueryPlan, device: torch.device) -> torch.Tensor:
+    """Segment tables on ``device`` (cached per plan: the upload happens once)."""
+    key = (id(plan), device.index)
+    hit = _TABLE_CACHE.get(key)
+    if hit is not None and hit[0] is plan:
+        return hit[1]
+    host_tab = np.concatenate([plan.seg_lo, plan.seg_hi, plan.mt_seg, plan.seg_first]).astype(np.int32)
+    tables = torch.from_numpy(host_tab).to(device)
+    if len(_TABLE_CACHE) > 512:
+        _TABLE_CACHE.clear()
+    _TABLE_CACHE[key] = (plan, tables)
+    return tables
+
+
+@dataclass
+class PageStore:
+    """Flat ragged page-token store on one device (what ``lis_maxsim_scores`` reads)."""
+    tokens: torch.Tensor            # [rows, 128] 16-bit
+    offsets: torch.Tensor           # int64 [np+1]
+    clamp: Optional[torch.Tensor]   # uint8 [np] or None
+    n_pages: int
+
+    @property
+    def n_rows(self) -> int:
+        return int(self.tokens.shape[0])
+
+
+def build_page_store(ps: TensorOrList, device: torch.device, dtype: torch.dtype, batch_size: int = 128) -> PageStore:
+    if isinstance(ps, torch.Tensor) and ps.dim() == 3:
+        n, s, d = ps.shape
+        if d != N.DIM:
+            raise ValueError(f"passages: embedding width {d} != {N.DIM}")
+        tokens = ps.to(device=device, dtype=dtype, non_blocking=True).contiguous().reshape(n * s, d)
+        offsets = torch.arange(0, (n + 1) * s, s, dtype=torch.int64, device=device) if s > 0 else \
+            torch.zeros(n + 1, dtype=torch.int64, device=device)
+        return PageStore(tokens, offsets, None, n)
+    pl = _as_list(ps)
+    for t in pl:
+        _check_rows(t, "passage")
+    _common_dtype(pl, "passages")
+    lens = np.asarray([int(t.shape[0]) for t in pl], dtype=np.int64)
+    host = [t for t in pl if t.device.type == "cpu"]
+    if len(host) == len(pl):
+        tokens = torch.cat(pl, dim=0).to(device=device, dtype=dtype, non_blocking=True)
+    else:
+        tokens = torch.cat([t.to(device, non_blocking=True) for t in pl], dim=0).to(dtype)
+    offsets = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)).to(device, non_blocking=True)
+    flags = clamp_flags(lens, batch_size)
+    clamp = torch.from_numpy(flags).to(device, non_blocking=True) if flags.any() else None
+    return PageStore(tokens.contiguous(), offsets, clamp, len(pl))
+
+
+def maxsim_scores_device(pq: PackedQueries, store: PageStore, round_mode: str = "f32",
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Run K1 (+ the segment reduction when a query was split).  Returns device fp32 [nq, np]."""
+    lib = N.load()
+    if round_mode not in _ROUND:
+        raise ValueError(f"round_mode must be one of {sorted(_ROUND)}")
+    if store.tokens.dtype != pq.dtype:
+        raise ValueError(f"queries are {pq.dtype} but pages are {store.tokens.dtype}")
+    device = pq.rows.device
+    plan = pq.plan
+    npg = store.n_pages
+    seg_lo, seg_hi, mt_seg, seg_first = pq.table_ptrs()
+    direct = plan.direct
+    rm = _ROUND[round_mode]
+    if out is None:
+        out = torch.empty((plan.nq, npg), dtype=torch.float32, device=device)
+    seg_out = out if direct else torch.empty((plan.n_seg, npg), dtype=torch.float32, device=device)
+    st = _stream(device)
+    N.check(lib.lis_maxsim_scores(pq.rows.data_ptr(), pq.rows.shape[0], seg_lo, seg_hi, mt_seg, plan.n_seg,
+                                  plan.n_mtiles, store.tokens.data_ptr(), store.n_rows, store.offsets.data_ptr(),
+                                  _ptr(store.clamp), npg, _DTYPES[pq.dtype], rm if direct else rm | N.ROUND_DEFER_SUM,
+                                  seg_out.data_ptr(), seg_out.stride(0), st))
+    if not direct:
+        N.check(lib.lis_reduce_segments(seg_out.data_ptr(), seg_out.stride(0), seg_first, plan.nq, npg,
+                                        rm, _DTYPES[pq.dtype], out.data_ptr(), out.stride(0), st))
+    return out
+
+
+def score_multi_vector(qs: TensorOrList, ps: TensorOrList, batch_size: int = 128,
+                       device: Union[str, torch.device, None] = None, *, round_mode: str = "reference",
+                       return_device: bool = False) -> torch.Tensor:
+    """``score[b, c] = sum_n max_s <qs[b][n], ps[c][s]>`` -- same signature, zero-padding semantics,
+    error behaviour and CPU-float32 ``[len(qs), len(ps)]`` result as colpali-engine's
+    ``score_multi_vector`` (05_experiment02.py:214).
+
+    ``round_mode="reference"`` (default) reproduces what torch does to 16-bit inputs (per-token max
+    and final sum rounded to the input dtype); ``"f32"`` keeps fp32 throughout (the more accurate
+    number; within 1e-4 of the fp32-widened reference).  ``batch_size`` only matters through the
+    padding it implies in the reference: a page shorter than the longest page of its block has its
+    per-token max clamped at 0.  Inputs may live on any device; the corpus is not copied when it is
+    already a contiguous CUDA tensor.
+    """
+    if len(qs) == 0:
+        raise ValueError("No queries provided")
+    if len(ps) == 0:
+        raise ValueError("No passages provided")
+    dev = resolve_device(device)
+    N.check(N.load().lis_device_supported(dev.index))
+    with torch.cuda.device(dev):
+        pq = pack_queries(qs, dev)
+        store = build_page_store(ps, dev, pq.dtype, batch_size)
+        if store.n_rows == 0:
+            raise ValueError("No passages provided")
+        scores = maxsim_scores_device(pq, store, round_mode)
+        if return_device:
+            return scores
+        return scores.cpu()

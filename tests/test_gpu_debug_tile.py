@@ -1,0 +1,41 @@
+"""First thing to run on a GPU: the raw TMA -> UMMA -> TMEM path against a plain matmul.
+If this fails, everything downstream is noise; the printed pattern says which descriptor is wrong."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tile_n", [128, 256])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_sim_tile_matches_matmul(lis, tile_n, dtype):
+    from importlib import import_module
+
+    N = import_module("multi-modal_colpali_b200._native")
+    lib = N.load()
+    g = torch.Generator().manual_seed(7)
+    q = torch.randn(128, 128, generator=g).to(dtype).cuda()
+    p = torch.randn(tile_n + 40, 128, generator=g).to(dtype).cuda()
+    out = torch.full((128, tile_n), float("nan"), dtype=torch.float32, device="cuda")
+    rc = lib.lis_debug_sim_tile(q.data_ptr(), 128, p.data_ptr(), p.shape[0], 0 if dtype == torch.bfloat16 else 1,
+                                tile_n, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    N.check(rc)
+    torch.cuda.synchronize()
+    ref = q.float() @ p[:tile_n].float().T
+    err = (out - ref).abs()
+    if not (err.max() < 1e-3):
+        bad = (err > 1e-3)
+        print("max err", err.max().item(), "bad fraction", bad.float().mean().item())
+        print("bad rows", bad.any(1).nonzero().flatten()[:16].tolist(), "bad cols", bad.any(0).nonzero().flatten()[:16].tolist())
+        print("out[0,:8]", out[0, :8].tolist(), "ref[0,:8]", ref[0, :8].tolist())
+        # does the output match a permutation of K chunks / rows?  quick probes
+        for name, alt in {
+            "first 64 k only": q.float()[:, :64] @ p[:tile_n].float()[:, :64].T,
+            "last 64 k only": q.float()[:, 64:] @ p[:tile_n].float()[:, 64:].T,
+            "first 16 k only": q.float()[:, :16] @ p[:tile_n].float()[:, :16].T,
+            "transposed": (q.float() @ p[:tile_n].float().T).T[:128, :tile_n] if tile_n == 128 else ref,
+        }.items():
+            print(name, (out - alt).abs().max().item())
+    assert err.max() < 1e-3

@@ -1,0 +1,330 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): 1e-4 absolute against the oracle on the same 16-bit inputs
+widened to fp32 (``round_mode="f32"``); 1e-2 absolute against the oracle run in bf16 like the
+reference does (``round_mode="reference"``), where agreement is in fact expected to be <= 1 bf16 ulp.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-4
+TOL_BF16 = 1e-2
+
+
+def unit(x):
+    return x / x.norm(dim=-1, keepdim=True)
+
+
+def rand_unit(gen, *shape, dtype=torch.bfloat16):
+    return unit(torch.randn(*shape, generator=gen)).to(dtype)
+
+
+def ragged(gen, lens, dtype=torch.bfloat16):
+    return [rand_unit(gen, int(n), 128, dtype=dtype) if n > 0 else torch.zeros(0, 128, dtype=dtype) for n in lens]
+
+
+def assert_topk_equiv(got_ids, got_scores, full_scores, tol):
+    """north_star: top-k ids identical to the oracle's except for ties inside the tolerance."""
+    k = len(got_ids)
+    best = torch.sort(full_scores, descending=True).values[:k]
+    assert len(set(got_ids)) == k
+    for j, (i, s) in enumerate(zip(got_ids, got_scores)):
+        assert abs(full_scores[i].item() - s) <= tol, (j, i, s, full_scores[i].item())
+        assert abs(best[j].item() - s) <= tol, (j, i, s, best[j].item())
+
+
+def check_both_modes(lis, oracle, qs, ps, batch_size=128):
+    want32 = oracle.score_multi_vector_widened(qs, ps, batch_size=batch_size)
+    got32 = lis.score_multi_vector(qs, ps, batch_size=batch_size, round_mode="f32")
+    assert got32.dtype == torch.float32 and got32.device.type == "cpu"
+    assert got32.shape == want32.shape
+    err32 = (got32 - want32).abs().max().item()
+    assert err32 <= TOL_F32, f"f32 mode: max abs err {err32}"
+    # the reference's own 16-bit path (torch CPU) and its rounding model
+    want16 = oracle.score_multi_vector(qs, ps, batch_size=batch_size)
+    got16 = lis.score_multi_vector(qs, ps, batch_size=batch_size)  # default round_mode="reference"
+    err16 = (got16 - want16).abs().max().item()
+    assert err16 <= TOL_BF16, f"reference mode: max abs err {err16}"
+    return err32, err16
+
+
+# ---------------------------------------------------------------------------------------------
+def test_config1_colpali_shapes(lis, oracle):
+    """BASELINE configs[0]: 1 query x 16 tokens vs 1000 pages x 1030 tokens (seeds from SURVEY 8d)."""
+    q = rand_unit(torch.Generator().manual_seed(1001), 1, 16, 128)
+    p = rand_unit(torch.Generator().manual_seed(2001), 1000, 1030, 128)
+    err32, err16 = check_both_modes(lis, oracle, q, p)
+    # reference-rounding mode should reproduce torch's bf16 path essentially bit-for-bit
+    want = oracle.score_multi_vector_bf16_rounding_model(q, p)
+    got = lis.score_multi_vector(q, p)
+    ulp = 2.0 ** (math.floor(math.log2(want.abs().max().item())) - 7)
+    assert (got - want).abs().max().item() <= ulp
+    assert ((got - want) == 0).float().mean().item() > 0.98
+
+
+def test_many_queries_multi_mtile(lis, oracle):
+    """32 queries x 20 tokens (BASELINE configs[1] query shape: 640 rows = 5 M tiles, cut queries)."""
+    q = rand_unit(torch.Generator().manual_seed(1002), 32, 20, 128)
+    p = rand_unit(torch.Generator().manual_seed(2002), 600, 257, 128)
+    check_both_modes(lis, oracle, q, p)
+
+
+def test_ragged_lists_and_zero_padding(lis, oracle):
+    g = torch.Generator().manual_seed(3)
+    q_lens = [5, 20, 33, 128, 130, 300, 1, 17]
+    p_lens = [1, 2, 3, 31, 32, 33, 64, 127, 128, 129, 255, 256, 257, 300, 511, 513, 700, 768, 40, 7] * 9
+    qs, ps = ragged(g, q_lens), ragged(g, p_lens)
+    for bs in (128, 16, 7):
+        check_both_modes(lis, oracle, qs, ps, batch_size=bs)
+
+
+def test_negative_sims_are_clamped_like_zero_padding(lis, oracle):
+    """A short page whose real tokens all point away from the query: the reference's pad rows give 0."""
+    g = torch.Generator().manual_seed(4)
+    q = rand_unit(g, 1, 8, 128)
+    away = (-q[0, :3]).clone()                       # 3 tokens anti-aligned with query tokens 0..2
+    long_page = rand_unit(g, 50, 128)
+    ps = [away, long_page]
+    want = oracle.score_multi_vector_widened(q, ps)
+    got = lis.score_multi_vector(q, ps, round_mode="f32")
+    assert (got - want).abs().max().item() <= TOL_F32
+    # and without padding (a single page is its own longest page) the negative max survives
+    want1 = oracle.score_multi_vector_widened(q, [away])
+    got1 = lis.score_multi_vector(q, [away], round_mode="f32")
+    assert (got1 - want1).abs().max().item() <= TOL_F32
+    assert want1.item() < want[0, 0].item()
+
+
+def test_padded_tensor_inputs_left_and_right(lis, oracle):
+    """ColQwen pads on the left, ColPali on the right; encoders zero the padded rows."""
+    g = torch.Generator().manual_seed(5)
+    p = rand_unit(g, 70, 90, 128)
+    for i in range(70):
+        n_pad = int(torch.randint(0, 60, (1,), generator=g))
+        if i % 2:
+            p[i, :n_pad] = 0
+        else:
+            p[i, 90 - n_pad:] = 0
+    q = rand_unit(g, 3, 24, 128)
+    q[1, 20:] = 0
+    check_both_modes(lis, oracle, q, p)
+
+
+def test_known_answers(lis):
+    """Analytic cases."""
+    eye = torch.eye(128)
+    q = eye[:10].to(torch.bfloat16).unsqueeze(0)                      # 10 one-hot query tokens
+    pages = [eye[:64].to(torch.bfloat16), eye[5:69].to(torch.bfloat16), eye[64:].to(torch.bfloat16)]
+    got = lis.score_multi_vector(q, pages, round_mode="f32")
+    assert got.tolist() == [[10.0, 5.0, 0.0]]
+    # appending a zero query token / permuting page tokens changes nothing
+    q0 = torch.cat([q, torch.zeros(1, 1, 128, dtype=torch.bfloat16)], dim=1)
+    perm = [p[torch.randperm(p.shape[0], generator=torch.Generator().manual_seed(1))] for p in pages]
+    assert torch.equal(lis.score_multi_vector(q0, perm, round_mode="f32"), got)
+
+
+def test_empty_inputs_raise(lis):
+    x = torch.zeros(1, 4, 128, dtype=torch.bfloat16)
+    with pytest.raises(ValueError, match="No queries provided"):
+        lis.score_multi_vector([], x)
+    with pytest.raises(ValueError, match="No passages provided"):
+        lis.score_multi_vector(x, [])
+
+
+def test_fp16_inputs(lis, oracle):
+    g = torch.Generator().manual_seed(6)
+    q = rand_unit(g, 4, 30, 128, dtype=torch.float16)
+    p = rand_unit(g, 300, 100, 128, dtype=torch.float16)
+    want = oracle.score_multi_vector_widened(q, p)
+    got = lis.score_multi_vector(q, p, round_mode="f32")
+    assert (got - want).abs().max().item() <= TOL_F32
+
+
+def test_all_tilings_agree_bitwise(lis, oracle):
+    """Every (tile_n, group) instantiation computes the same numbers."""
+    from importlib import import_module
+
+    N = import_module("multi-modal_colpali_b200._native")
+    lib = N.load()
+    g = torch.Generator().manual_seed(8)
+    qs = ragged(g, [20] * 29 + [60])          # 640 rows -> 5 M tiles
+    ps = ragged(g, [int(x) for x in torch.randint(1, 400, (500,), generator=g)])
+    want = oracle.score_multi_vector_widened(qs, ps)
+    base = None
+    try:
+        for nt, grp in [(256, 1), (256, 2), (256, 3), (128, 1), (128, 2), (128, 3), (128, 4), (128, 5)]:
+            N.check(lib.lis_set_tuning(nt, grp, 0))
+            got = lis.score_multi_vector(qs, ps, round_mode="f32")
+            assert (got - want).abs().max().item() <= TOL_F32, (nt, grp)
+            if base is None:
+                base = got
+            assert torch.equal(got, base), (nt, grp)
+        N.check(lib.lis_set_tuning(0, 0, 3))   # 3 CTAs only: long per-CTA page ranges
+        got = lis.score_multi_vector(qs, ps, round_mode="f32")
+        assert torch.equal(got, base)
+    finally:
+        lib.lis_set_tuning(0, 0, 0)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_topk_matches_oracle_with_ties(lis, oracle):
+    g = torch.Generator().manual_seed(9)
+    scores = torch.randn(5, 20000, generator=g)
+    scores[:, 1000:1010] = scores[:, :10]              # exact ties
+    scores[2, 77] = float("nan")
+    want_v, want_i = oracle.topk(torch.nan_to_num(scores, nan=float("-inf")), 100)
+    got_v, got_i = lis.topk_device(scores.cuda(), 100)
+    assert torch.equal(got_i.cpu(), want_i)
+    assert torch.equal(got_v.cpu(), want_v)
+    # k larger than the row, and a tiny row
+    got_v, got_i = lis.topk_device(scores[:, :7].contiguous().cuda(), 10)
+    assert (got_i[:, 7:] == -1).all() and torch.isinf(got_v[:, 7:]).all()
+    want_v, want_i = oracle.topk(torch.nan_to_num(scores[:, :7], nan=float("-inf")), 7)
+    assert torch.equal(got_i[:, :7].cpu(), want_i)
+
+
+def test_topk_large_row_multi_pass(lis, oracle):
+    g = torch.Generator().manual_seed(10)
+    scores = torch.randn(2, 300_000, generator=g)
+    for k in (10, 1024):
+        want_v, want_i = oracle.topk(scores, k)
+        got_v, got_i = lis.topk_device(scores.cuda(), k, id_base=5_000_000_000)
+        assert torch.equal(got_i.cpu() - 5_000_000_000, want_i)
+        assert torch.equal(got_v.cpu(), want_v)
+
+
+def test_merge_topk(lis, oracle):
+    g = torch.Generator().manual_seed(11)
+    parts = []
+    for r in range(4):
+        v = torch.randn(3, 10, generator=g).sort(dim=1, descending=True).values
+        i = torch.randint(0, 1 << 40, (3, 10), generator=g)
+        if r == 3:
+            v[:, 6:] = float("-inf"); i[:, 6:] = -1      # a short shard pads with -1
+        parts.append((v, i))
+    want_v, want_i = oracle.merge_topk(parts, 10)
+    got_v, got_i = lis.merge_topk_device(torch.cat([p[0] for p in parts], 1).cuda(),
+                                         torch.cat([p[1] for p in parts], 1).cuda(), 10)
+    assert torch.equal(got_i.cpu(), want_i) and torch.equal(got_v.cpu(), want_v)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_index_search_matches_oracle(lis, oracle):
+    g = torch.Generator().manual_seed(12)
+    p_lens = [int(x) for x in torch.randint(200, 769, (400,), generator=g)]
+    ps = ragged(g, p_lens)
+    qs = ragged(g, [32, 16, 45])
+    idx = lis.LateInteractionIndex(sum(p_lens), len(ps))
+    ids = idx.add(ps[:150], ids=list(range(1000, 1150)))
+    idx.add(ps[150:], ids=list(range(5000, 5250)))
+    assert len(idx) == 400 and idx.num_rows == sum(p_lens)
+    all_ids = torch.tensor(list(range(1000, 1150)) + list(range(5000, 5250)))
+    want = oracle.score_multi_vector_widened(qs, [p for p in ps], batch_size=10 ** 9)
+    # an index built without zero_pad_block has mask (no-clamp) semantics; with unit-norm random
+    # pages every query token has a positive best match, so both semantics coincide here
+    full = idx.scores(qs).cpu()
+    assert (full - want).abs().max().item() <= TOL_F32
+    want_v, want_i = oracle.topk(full, 10)
+    got_v, got_i = idx.search(qs, 10)
+    assert torch.equal(got_i, all_ids[want_i]) and torch.equal(got_v, want_v)
+    idx.close()
+
+
+def test_index_synthetic_fill_and_planted_needles(lis, oracle):
+    idx = lis.LateInteractionIndex(20000 * 64 + 1000, 20010)
+    idx.fill_synthetic(20000, 64, seed=2004, id_base=0)
+    rows = idx.read_rows(0, 64 * 20)
+    assert torch.allclose(rows.float().norm(dim=-1), torch.ones(64 * 20), atol=1e-2)
+    assert rows.float().std().item() == pytest.approx(1 / math.sqrt(128), rel=0.1)
+    g = torch.Generator().manual_seed(1004)
+    q = rand_unit(g, 1, 16, 128)
+    needles = [unit(0.9 * q[0].float() + 0.02 * torch.randn(16, 128, generator=g)).to(torch.bfloat16) for _ in range(5)]
+    idx.add(needles, ids=[900001 + i for i in range(5)])
+    v, i = idx.search(q, 10)
+    assert sorted(i[0, :5].tolist()) == [900001 + j for j in range(5)]
+    assert v[0, 4].item() > v[0, 5].item() + 1.0
+    # oracle check on a slice: first 20 synthetic pages
+    want = oracle.score_multi_vector_widened(q, rows.reshape(20, 64, 128))
+    got = idx.scores(q).cpu()[:, :20]
+    assert (got - want).abs().max().item() <= TOL_F32
+    idx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hidden", [768, 2048])
+def test_projection_head(lis, oracle, hidden):
+    g = torch.Generator().manual_seed(13)
+    h = torch.randn(3, 301, hidden, generator=g).to(torch.bfloat16)
+    w = (torch.randn(128, hidden, generator=g) / math.sqrt(hidden)).to(torch.bfloat16)
+    b = (0.1 * torch.randn(128, generator=g)).to(torch.bfloat16)
+    mask = (torch.rand(3, 301, generator=g) > 0.2).long()
+    want = oracle.project_normalize(h.float(), w.float(), b.float(), mask.float())
+    got = lis.project_normalize(h.cuda(), w.cuda(), b.cuda(), mask.cuda()).cpu()
+    assert got.dtype == torch.bfloat16 and got.shape == (3, 301, 128)
+    assert (got.float() - want).abs().max().item() <= 4e-3      # bf16 output rounding of values <= 1
+    assert (got[mask == 0] == 0).all()
+    got_nb = lis.project_normalize(h.cuda(), w.cuda()).cpu()
+    want_nb = oracle.project_normalize(h.float(), w.float(), None, None)
+    assert (got_nb.float() - want_nb).abs().max().item() <= 4e-3
+
+
+# ---------------------------------------------------------------------------------------------
+class _FakeBatch(dict):
+    def to(self, device):
+        return _FakeBatch({k: v.to(device) for k, v in self.items()})
+
+
+class _FakeProcessor:
+    def __init__(self, table):
+        self.table = table
+
+    def process_queries(self, queries):
+        return _FakeBatch(emb=torch.stack([self.table[q] for q in queries]))
+
+
+class _FakeModel:
+    device = torch.device("cuda", 0)
+
+    def __call__(self, emb):
+        return emb
+
+
+def test_reference_api_shapes(lis, oracle):
+    g = torch.Generator().manual_seed(14)
+    pages = rand_unit(g, 40, 50, 128)
+    dataset = [{"embedding": pages[i], "doc_id": i // 4, "page_id": i % 4, "file_name": f"f{i // 4}.pdf"} for i in range(40)]
+    images = {f"f{d}.pdf": {p: f"img-{d}-{p}" for p in range(4)} for d in range(10)}
+    table = {"q0": rand_unit(g, 12, 128), "q1": rand_unit(g, 12, 128)}
+    out = lis.score_results(["q0", "q1"], _FakeProcessor(table), _FakeModel(), dataset, images, top_k=5)
+    want = oracle.score_multi_vector(torch.stack([table["q0"], table["q1"]]), pages)
+    assert [len(r) for r in out] == [5, 5]
+    for q in range(2):
+        ids = [r["doc_id"] * 4 + r["page_id"] for r in out[q]]
+        assert_topk_equiv(ids, [r["score"] for r in out[q]], want[q], TOL_BF16)
+        assert all(r["image"] == images[r["file_name"]][r["page_id"]] for r in out[q])
+        assert all(r["file_name"] == f"f{r['doc_id']}.pdf" for r in out[q])
+
+    client = lis.MaxSimClient(capacity_rows=4096, capacity_pages=64)
+    lis.ensure_colpali_collection(client, "colpali")
+    pts = [lis.PointStruct(id=f"p{i}", vector=pages[i].float().tolist(),
+                           payload={"document_name": f"f{i // 4}.pdf", "page_no": i % 4, "img_link": f"l{i}",
+                                    "username": "ann" if i % 2 else "bob"}) for i in range(40)]
+    client.upsert("colpali", pts[:25])
+    client.upsert("colpali", pts[25:])
+    assert client.count("colpali") == 40
+    want32 = oracle.score_multi_vector_widened(table["q0"][None], pages)[0]
+    res = lis.retrieve_colpali("q0", _FakeProcessor(table), _FakeModel(), client, "", "colpali", 5)
+    ids = [int(p.id[1:]) for p in res.points]
+    assert_topk_equiv(ids, [p.score for p in res.points], want32, 2e-2)   # cosine re-normalisation in bf16
+    assert all(p.payload["img_link"] == f"l{i}" for p, i in zip(res.points, ids))
+    res = lis.retrieve_colpali("q0", _FakeProcessor(table), _FakeModel(), client, "ann", "colpali", 5)
+    odd = want32.clone(); odd[0::2] = float("-inf")
+    ids = [int(p.id[1:]) for p in res.points]
+    assert len(ids) == 5 and all(i % 2 == 1 for i in ids)
+    assert_topk_equiv(ids, [p.score for p in res.points], odd, 2e-2)
+    assert all(p.payload["username"] == "ann" for p in res.points)
