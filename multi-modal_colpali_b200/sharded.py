@@ -49,8 +49,9 @@ def gather_candidates(scores: torch.Tensor, ids: torch.Tensor, group=None) -> Tu
     packed = torch.empty((nq, 2, k), dtype=torch.int64, device=scores.device)
     packed[:, 0, :] = scores.contiguous().view(torch.int32).to(torch.int64)
     packed[:, 1, :] = ids
-    out = torch.empty((world, nq, 2, k), dtype=torch.int64, device=scores.device)
-    dist.all_gather_into_tensor(out, packed, group=group)
+    flat = torch.empty((world * nq, 2, k), dtype=torch.int64, device=scores.device)
+    dist.all_gather_into_tensor(flat, packed, group=group)
+    out = flat.view(world, nq, 2, k)
     all_s = out[:, :, 0, :].to(torch.int32).view(torch.float32).permute(1, 0, 2).reshape(nq, world * k)
     all_i = out[:, :, 1, :].permute(1, 0, 2).reshape(nq, world * k)
     return all_s.contiguous(), all_i.contiguous()

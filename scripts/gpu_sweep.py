@@ -1,0 +1,77 @@
+"""Tiling / regime sweep on one B200: K1 alone, device-resident inputs, CUDA-event timing.
+Writes one JSON object per line to gpurun_out/sweep.jsonl."""
+import importlib
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+lis = importlib.import_module("multi-modal_colpali_b200")
+native = importlib.import_module("multi-modal_colpali_b200._native")
+scoring = importlib.import_module("multi-modal_colpali_b200.scoring")
+lib = native.load()
+dev = torch.device("cuda", 0)
+out = open(ROOT / "gpurun_out" / "sweep.jsonl", "a")
+
+
+def unit(x):
+    return x / x.norm(dim=-1, keepdim=True)
+
+
+def time_k1(pq, store, iters=5, warm=2):
+    scores = torch.empty((pq.plan.nq, store.n_pages), dtype=torch.float32, device=dev)
+    for _ in range(warm):
+        scoring.maxsim_scores_device(pq, store, "f32", out=scores)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        scoring.maxsim_scores_device(pq, store, "f32", out=scores)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts), sum(ts) / len(ts)
+
+
+def report(name, nq, qtok, pages, ptok, tilings, ragged=None):
+    g = torch.Generator().manual_seed(1)
+    q = unit(torch.randn(nq, qtok, 128, generator=g)).to(torch.bfloat16).to(dev)
+    pq = scoring.pack_queries(q, dev)
+    rows = pages * ptok if ragged is None else int(sum(ragged))
+    idx = lis.LateInteractionIndex(rows, pages, device=dev)
+    idx.fill_synthetic(pages, ptok if ragged is None else ragged, seed=7)
+    store = idx._as_store()
+    flops = 2.0 * nq * qtok * 128 * rows
+    byts = rows * 256.0
+    for nt, grp in tilings:
+        native.check(lib.lis_set_tuning(nt, grp, 0))
+        best, mean = time_k1(pq, store)
+        rec = {"case": name, "nq": nq, "qtok": qtok, "pages": pages, "ptok": ptok, "rows": rows, "tile_n": nt,
+               "group": grp, "ms_best": best, "ms_mean": mean, "tflops": flops / (best * 1e-3) / 1e12,
+               "gbs": byts / (best * 1e-3) / 1e9, "pairs_per_s": nq * pages / (best * 1e-3)}
+        print(json.dumps(rec), flush=True)
+        out.write(json.dumps(rec) + "\n")
+        out.flush()
+    lib.lis_set_tuning(0, 0, 0)
+    idx.close()
+    del store, idx
+    torch.cuda.empty_cache()
+
+
+which = sys.argv[1:] or ["c2", "hbm", "c5", "c3"]
+if "c2" in which:
+    report("c2_32x20_vs_100kx1030", 32, 20, 100_000, 1030,
+           [(0, 0), (128, 5), (128, 4), (128, 3), (128, 2), (128, 1), (256, 3), (256, 2), (256, 1)])
+if "hbm" in which:
+    report("single_query_16tok_vs_100kx1030", 1, 16, 100_000, 1030, [(0, 0), (256, 1), (128, 1)])
+    report("4q_32tok_vs_100kx1030", 4, 32, 100_000, 1030, [(0, 0), (128, 1)])
+    report("8q_32tok_vs_100kx1030", 8, 32, 100_000, 1030, [(0, 0), (128, 2)])
+if "c5" in which:
+    report("c5_slice_1024x32_vs_20kx1030", 1024, 32, 20_000, 1030, [(0, 0), (128, 4), (256, 3), (256, 2)])
+if "c3" in which:
+    lens = torch.randint(256, 769, (200_000,), generator=torch.Generator().manual_seed(3003)).tolist()
+    report("c3_slice_1q32_vs_200k_ragged256-768", 1, 32, 200_000, 0, [(0, 0), (128, 1)], ragged=lens)

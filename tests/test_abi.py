@@ -1,0 +1,109 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/lis.h declares;
+host-only entry points (query planning, argument validation) behave as documented."""
+import ctypes as C
+import importlib
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def native():
+    return importlib.import_module("multi-modal_colpali_b200._native")
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "lis.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lis_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound(native):
+    lib = native.load()
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"liblis.so does not export {n}"
+        assert n in native.SIGNATURES, f"_native.py does not bind {n}"
+    assert set(native.SIGNATURES) == set(names)
+    assert lib.lis_abi_version() == 1
+
+
+def test_no_torch_types_in_abi():
+    """Signatures are plain C: strip comments, then no C++/torch type may remain."""
+    text = (ROOT / "include" / "lis.h").read_text()
+    code = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    for banned in ("torch", "at::", "std::", "Tensor", "template", "class "):
+        assert banned not in code, banned
+
+
+def ref_plan(lens):
+    """Independent restatement of the segmentation rule."""
+    segs, row = [], 0
+    for q, n in enumerate(lens):
+        while n > 0:
+            take = min(n, 128 - row % 128)
+            segs.append((q, row, row + take))
+            row += take
+            n -= take
+    return segs, (row + 127) // 128
+
+
+@pytest.mark.parametrize("lens", [[16], [20] * 32, [32] * 1024, [100, 100, 300, 0, 5], [128, 128], [1] * 300, [0, 0, 7]])
+def test_plan_queries(lis, lens):
+    plan = lis.plan_queries(lens)
+    segs, tiles = ref_plan(lens)
+    assert plan.n_seg == len(segs) and plan.n_mtiles == tiles and plan.nq == len(lens)
+    assert list(zip(plan.seg_query.tolist(), plan.seg_lo.tolist(), plan.seg_hi.tolist())) == segs
+    for t in range(tiles):
+        inside = [s for s in range(plan.n_seg) if plan.seg_lo[s] // 128 == t]
+        assert list(range(plan.mt_seg[t], plan.mt_seg[t + 1])) == inside
+    for s in range(plan.n_seg):      # a segment never straddles an M tile
+        assert plan.seg_lo[s] // 128 == (plan.seg_hi[s] - 1) // 128
+    for q in range(len(lens)):
+        mine = list(range(plan.seg_first[q], plan.seg_first[q + 1]))
+        assert sum(plan.seg_hi[s] - plan.seg_lo[s] for s in mine) == lens[q]
+    assert plan.direct == (len(segs) == len(lens))
+
+
+def test_plan_queries_errors(native):
+    lib = native.load()
+    lens = np.asarray([4, -1], np.int32)
+    n_mt = C.c_int64()
+    rc = lib.lis_plan_queries(lens.ctypes.data, 2, 0, None, None, None, 0, None, C.byref(n_mt))
+    assert rc == native.LIS_E_INVALID
+    assert "negative length" in native.last_error()
+    with pytest.raises(ValueError):
+        native.check(rc)
+    # capacity too small
+    lens = np.asarray([200], np.int32)
+    buf = np.zeros(1, np.int32)
+    rc = lib.lis_plan_queries(lens.ctypes.data, 1, 1, buf.ctypes.data, buf.ctypes.data, buf.ctypes.data, 8,
+                              np.zeros(8, np.int32).ctypes.data, C.byref(n_mt))
+    assert rc == native.LIS_E_INVALID and "capacity" in native.last_error()
+
+
+def test_argument_validation_without_gpu(native):
+    lib = native.load()
+    assert lib.lis_set_tuning(64, 0, 0) == native.LIS_E_INVALID
+    assert lib.lis_set_tuning(256, 4, 0) == native.LIS_E_INVALID
+    assert lib.lis_set_tuning(0, 0, 0) == 0
+    assert lib.lis_maxsim_scores(None, 0, None, None, None, 0, 0, None, 0, None, None, 0, 0, 0, None, 0, None) \
+        == native.LIS_E_INVALID
+    assert "null pointer" in native.last_error()
+    assert lib.lis_topk(None, 0, 1, 1, None, 0, 5000, None, None, None, 0, None) == native.LIS_E_INVALID
+    assert lib.lis_index_num_pages(None) == 0
+
+
+def test_topk_workspace_sizes(native):
+    lib = native.load()
+    assert lib.lis_topk_workspace_bytes(1, 100, 10) == 256           # one chunk: no scratch
+    a = lib.lis_topk_workspace_bytes(1, 500_000, 10)
+    b = lib.lis_topk_workspace_bytes(32, 500_000, 10)
+    c = lib.lis_topk_workspace_bytes(1, 500_000, 100)
+    assert 0 < a < b and a < c
+    assert lib.lis_topk_workspace_bytes(1, 100, 5000) == 0           # k out of range

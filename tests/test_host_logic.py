@@ -1,0 +1,81 @@
+"""Host-side logic of the drop-in surface that needs no GPU."""
+import numpy as np
+import pytest
+import torch
+
+
+def test_clamp_flags_follow_reference_batching(lis, oracle):
+    """clamp flag == "pad_sequence added zero rows to this page inside its batch"."""
+    g = torch.Generator().manual_seed(0)
+    lens = [int(x) for x in torch.randint(1, 9, (23,), generator=g)]
+    for bs in (128, 8, 5, 1):
+        flags = lis.clamp_flags(lens, bs)
+        for j in range(0, len(lens), bs):
+            blk = lens[j:j + bs]
+            assert flags[j:j + bs].tolist() == [int(n < max(blk)) for n in blk]
+    # semantic check against the oracle: the clamp only matters when it changes the result
+    q = torch.randn(1, 4, 128, generator=g)
+    pages = [-q[0, :2], torch.randn(6, 128, generator=g)]
+    padded = oracle.score_multi_vector(q, pages)[0, 0]
+    alone = oracle.score_multi_vector(q, pages[:1])[0, 0]
+    assert lis.clamp_flags([2, 6]).tolist() == [1, 0] and padded > alone
+
+
+def test_no_cpu_fallback(lis):
+    x = torch.zeros(1, 4, 128, dtype=torch.bfloat16)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        lis.score_multi_vector(x, x)
+    with pytest.raises(RuntimeError, match="CUDA only|no CPU fallback"):
+        lis.score_multi_vector(x, x, device="cpu")
+    with pytest.raises(RuntimeError):
+        lis.project_normalize(torch.zeros(2, 64, dtype=torch.bfloat16), torch.zeros(128, 64, dtype=torch.bfloat16))
+
+
+def test_empty_inputs_raise_before_touching_the_gpu(lis):
+    x = torch.zeros(1, 4, 128, dtype=torch.bfloat16)
+    with pytest.raises(ValueError, match="No queries provided"):
+        lis.score_multi_vector([], x)
+    with pytest.raises(ValueError, match="No passages provided"):
+        lis.score_multi_vector(x, [])
+
+
+def test_shard_ranges(lis):
+    for n, w in [(10, 3), (7, 8), (100_000, 8), (0, 2)]:
+        parts = [lis.shard_range(n, r, w) for r in range(w)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+        sizes = [b - a for a, b in parts]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        lis.shard_range(10, 3, 3)
+    lens = [5, 5, 5, 5, 100, 1, 1, 1]
+    parts = lis.balanced_shard_ranges(lens, 2)
+    assert parts == [(0, 4), (4, 8)]
+    rng = np.random.default_rng(0)
+    lens = rng.integers(256, 769, size=10_000)
+    parts = lis.balanced_shard_ranges(lens, 8)
+    assert parts[0][0] == 0 and parts[-1][1] == len(lens)
+    tok = [int(lens[a:b].sum()) for a, b in parts]
+    assert max(tok) / min(tok) < 1.01
+
+
+def test_filter_parsing():
+    import importlib
+
+    api = importlib.import_module("multi-modal_colpali_b200.reference_api")
+    f = {"must": [{"key": "username", "match": {"value": "ann"}}]}
+    assert api._filter_conditions(f) == [("username", "ann")]
+    assert api._filter_conditions(None) == []
+
+    class MV:  # qdrant-client style objects
+        def __init__(self, value): self.value = value
+
+    class FC:
+        def __init__(self, key, match): self.key, self.match = key, match
+
+    class F:
+        def __init__(self, must): self.must = must
+
+    assert api._filter_conditions(F([FC("username", MV("bob"))])) == [("username", "bob")]
