@@ -105,9 +105,10 @@ int lis_maxsim_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, cons
 int lis_reduce_segments(const float* seg_scores, int64_t ld_seg, const int32_t* seg_first, int64_t nq,
                         int64_t np, int round_mode, int dtype, float* out, int64_t ld_out, void* stream);
 
-/* Tuning / debug knobs (process-wide).  tile_n in {0 (auto), 128, 256}; group in {0 (auto), 1..5};
- * max_ctas 0 = one per SM.  Used by bench.py sweeps and tests; defaults are what ships. */
-int lis_set_tuning(int tile_n, int group, int max_ctas);
+/* Tuning / debug knobs (process-wide).  tile_n in {0 (auto), 128, 256}: page-token rows per MMA tile;
+ * group in {0 (auto), 1..5}: query M tiles resident per pass; max_ctas 0 = one per SM; epi_halves in
+ * {0 (auto), 1, 2}: 4 or 8 epilogue warps.  Used by sweeps and tests; the defaults are what ships. */
+int lis_set_tuning(int tile_n, int group, int max_ctas, int epi_halves);
 /* Number of kernels this library launched since load (all entry points). */
 int64_t lis_launch_count(void);
 

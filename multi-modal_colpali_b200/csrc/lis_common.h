@@ -20,6 +20,7 @@ struct Tuning {
   int tile_n = 0;
   int group = 0;
   int max_ctas = 0;
+  int epi_halves = 0;  // 0 = auto
 };
 extern Tuning g_tuning;
 

@@ -74,9 +74,9 @@ int sm_count(int device) {
 
 // ---------------------------------------------------------------------------------------------
 constexpr int kSmemBudget = 232448;  // 227 KB opt-in maximum per CTA on sm_100
-constexpr int kSmemTail = 2048;      // barriers + row-max exchange (1264 B used)
+constexpr int kSmemTail = 3072;      // barriers + row-max exchange (2288 B used)
 
-template <int NT, int G, bool DBG>
+template <int NT, int G, int EH, bool DBG>
 static int launch_maxsim(const CUtensorMap& tq, const CUtensorMap& tp, const MaxSimArgs& a, int grid,
                          cudaStream_t st) {
   const int stage = NT * kDim * 2;
@@ -87,7 +87,7 @@ static int launch_maxsim(const CUtensorMap& tq, const CUtensorMap& tp, const Max
     return LIS_E_INVALID;
   }
   const int smem = 1024 + G * kATileBytes + ns * stage + kSmemTail;
-  auto kern = maxsim_kernel<NT, G, DBG>;
+  auto kern = maxsim_kernel<NT, G, EH, DBG>;
   static bool configured[64] = {false};  // per template instantiation and device
   int dev = 0;
   LIS_CUDA_CHECK(cudaGetDevice(&dev));
@@ -95,7 +95,7 @@ static int launch_maxsim(const CUtensorMap& tq, const CUtensorMap& tp, const Max
     LIS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  kern<<<grid, kNumThreads, smem, st>>>(tq, tp, a, ns);
+  kern<<<grid, 64 + 128 * EH, smem, st>>>(tq, tp, a, ns);
   count_launch();
   LIS_CUDA_CHECK(cudaGetLastError());
   return LIS_OK;
@@ -104,11 +104,14 @@ static int launch_maxsim(const CUtensorMap& tq, const CUtensorMap& tp, const Max
 static int dispatch_maxsim(int nt, int g, const CUtensorMap& tq, const CUtensorMap& tp, const MaxSimArgs& a,
                            int grid, cudaStream_t st, bool dbg = false) {
   if (dbg) {
-    if (nt == 256 && g == 1) return launch_maxsim<256, 1, true>(tq, tp, a, grid, st);
-    if (nt == 128 && g == 1) return launch_maxsim<128, 1, true>(tq, tp, a, grid, st);
+    if (nt == 256 && g == 1) return launch_maxsim<256, 1, 2, true>(tq, tp, a, grid, st);
+    if (nt == 128 && g == 1) return launch_maxsim<128, 1, 1, true>(tq, tp, a, grid, st);
   }
-#define LIS_CASE(NT_, G_) \
-  if (nt == NT_ && g == G_) return launch_maxsim<NT_, G_, false>(tq, tp, a, grid, st);
+  const int eh = g_tuning.epi_halves ? g_tuning.epi_halves : 2;
+#define LIS_CASE(NT_, G_)                                                                   \
+  if (nt == NT_ && g == G_)                                                                 \
+    return eh == 2 ? launch_maxsim<NT_, G_, 2, false>(tq, tp, a, grid, st)                  \
+                   : launch_maxsim<NT_, G_, 1, false>(tq, tp, a, grid, st);
   LIS_CASE(256, 1) LIS_CASE(256, 2) LIS_CASE(256, 3)
   LIS_CASE(128, 1) LIS_CASE(128, 2) LIS_CASE(128, 3) LIS_CASE(128, 4) LIS_CASE(128, 5)
 #undef LIS_CASE
@@ -136,7 +139,9 @@ int lis_device_supported(int device) {
   return LIS_OK;
 }
 
-int lis_set_tuning(int tile_n, int group, int max_ctas) {
+int lis_set_tuning(int tile_n, int group, int max_ctas, int epi_halves) {
+  const int epi = epi_halves;
+  LIS_REQUIRE(epi >= 0 && epi <= 2, "epi_halves must be 0 (auto), 1 or 2");
   LIS_REQUIRE(tile_n == 0 || tile_n == 128 || tile_n == 256, "tile_n must be 0, 128 or 256");
   LIS_REQUIRE(group >= 0 && group <= 5, "group must be in 0..5");
   LIS_REQUIRE(!(tile_n == 256 && group > 3), "tile_n=256 supports group <= 3");
@@ -144,6 +149,7 @@ int lis_set_tuning(int tile_n, int group, int max_ctas) {
   g_tuning.tile_n = tile_n;
   g_tuning.group = group;
   g_tuning.max_ctas = max_ctas;
+  g_tuning.epi_halves = epi;
   return LIS_OK;
 }
 

@@ -6,12 +6,12 @@
 // body colpali-engine 0.3.13 == HF processing_colpali.py:360: einsum("bnd,csd->bcns").max(3).sum(2))
 // without ever materialising the [B,C,N,S] similarity tensor.
 //
-// Layout / roles (one persistent CTA per SM, 192 threads):
+// Layout / roles (one persistent CTA per SM, 192 or 320 threads):
 //   warp 0      TMA producer: query M tiles once (A operand, resident), then the CTA's slice of the
 //               page-token store as flat NT-row tiles through an NS-stage mbarrier ring (B operand).
 //   warp 1      tcgen05.mma issuer (one lane).  For every B tile: G MMAs (one per resident M tile),
 //               each 128 x NT x 128 (8 k-steps of 16), accumulators in a ring of 512/NT TMEM buffers.
-//   warps 2..5  epilogue: tcgen05.ld the accumulator (thread = query-token row), running per-page
+//   warps 2..   epilogue (4 or 8 warps): tcgen05.ld the accumulator (thread = query-token row), running per-page
 //               row max in registers (FMNMX3), page boundaries handled by column masks, then a
 //               segmented sum over the rows of each query through shared memory -> one fp32 per
 //               (query segment, page) to HBM.
@@ -51,10 +51,18 @@ __device__ __forceinline__ float round_to_input_dtype(float x, int is_bf16) {
   return is_bf16 ? __bfloat162float(__float2bfloat16_rn(x)) : __half2float(__float2half_rn(x));
 }
 
+// max of 32 accumulator columns and m: four independent FMNMX3 chains (the alu pipe has a 4-cycle
+// dependent-issue latency and the epilogue runs one or two warps per scheduler, so ILP matters)
 __device__ __forceinline__ float max32(const uint32_t (&v)[32], float m) {
+  float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < 32; i += 2) m = fmax3(m, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-  return m;
+  for (int i = 0; i < 32; i += 8) {
+    m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+    m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+    m2 = fmax3(m2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+    m3 = fmax3(m3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+  }
+  return fmax3(m0, m1, fmaxf(m2, m3));
 }
 __device__ __forceinline__ float max32_masked(const uint32_t (&v)[32], float m, int lo, int hi) {
 #pragma unroll
@@ -75,11 +83,12 @@ __device__ __forceinline__ int64_t lower_bound_off(const int64_t* off, int64_t n
   return lo;
 }
 
-template <int NT, int G, bool DBG>
-__global__ void __launch_bounds__(kNumThreads, 1)
+template <int NT, int G, int EH, bool DBG>
+__global__ void __launch_bounds__(64 + 128 * EH, 1)
 maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_p,
               const MaxSimArgs args, const int NS) {
   static_assert(NT == 128 || NT == 256, "tile_n");
+  static_assert(EH == 1 || EH == 2, "epilogue halves");
   constexpr int NACC = kTmemCols / NT;
   constexpr int kBStageBytes = NT * kDim * 2;
   constexpr int kBHalfBytes = NT * 128;
@@ -96,7 +105,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   uint64_t* acc_empty = acc_full + 4;                        // [NACC]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
   int64_t* range = reinterpret_cast<int64_t*>(tmem_slot + 2);  // [0]=page begin [1]=page end [2]=row0
-  float* srm = reinterpret_cast<float*>(range + 4);            // [2][128] row-max exchange
+  float* srm = reinterpret_cast<float*>(range + 4);            // [2][EH][128] row-max exchange
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -106,7 +115,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     tma_prefetch_desc(&tmap_p);
     mbar_init(q_full, 1);
     for (int s = 0; s < NS; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-    for (int a = 0; a < NACC; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, 4); }
+    for (int a = 0; a < NACC; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, 4 * EH); }
     fence_barrier_init();
     // This CTA's contiguous range of whole pages, balanced by token rows.
     const int64_t np = args.np;
@@ -194,24 +203,29 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2 .. 2+4*EH-1) =====================
+    // EH "column halves": with EH == 2 two warps share every TMEM lane quarter and each scans half
+    // of the tile's columns; their partial row maxima meet in shared memory when a page ends.
     const int quarter = warp & 3;             // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;         // 0 .. EH-1
     const int row = quarter * 32 + lane;      // query-token row inside the M tile
-    const int etid = row;                     // 0..127, also the "segment worker" index
     const int is_bf16 = args.is_bf16;
     const bool round_ref = (args.round_mode & 1) != 0;            // round the per-token max
     const bool round_sum = round_ref && (args.round_mode & 2) == 0;  // ... and the sum, unless deferred
+    constexpr int NCH = NT / 32;              // 32-column chunks per tile
+    constexpr int NOWN = NCH / EH;            // chunks scanned by this warp
+    const int c_lo = half * NOWN;
 
-    // segment handled by this thread in each resident M tile
+    // segment summed by this thread (half 0 only) in each resident M tile
     int seg_id[G], s_lo[G], s_hi[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       seg_id[g] = -1; s_lo[g] = 0; s_hi[g] = 0;
-      if (g < n_mt) {
+      if (g < n_mt && half == 0) {
         const int first = __ldg(args.mt_seg + args.mt0 + g);
         const int last = __ldg(args.mt_seg + args.mt0 + g + 1);
-        if (first + etid < last) {
-          seg_id[g] = first + etid;
+        if (first + row < last) {
+          seg_id[g] = first + row;
           s_lo[g] = __ldg(args.seg_lo + seg_id[g]) - (args.mt0 + g) * kMTile;
           s_hi[g] = __ldg(args.seg_hi + seg_id[g]) - (args.mt0 + g) * kMTile;
         }
@@ -223,18 +237,25 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     for (int g = 0; g < G; ++g) rm[g] = -INFINITY;
     int par = 0;
 
-    // Emit one finished page for M tile g: clamp / round the row max, exchange through smem,
-    // then the segment workers sum their rows in ascending row order (deterministic).
+    // Emit one finished page for M tile g: every epilogue thread publishes its partial row max,
+    // then the segment workers combine the halves (max), clamp / round like the reference, and sum
+    // their rows in ascending row order (deterministic).
     auto finish_page = [&](int g, int64_t p, float v) {
-      if (args.p_clamp != nullptr && __ldg(args.p_clamp + p)) v = fmaxf(v, 0.f);
-      if (round_ref) v = round_to_input_dtype(v, is_bf16);
-      srm[par * kMTile + row] = v;
-      named_bar_sync(1, kEpiThreads);
+      float* ex = srm + par * (EH * kMTile);
+      ex[half * kMTile + row] = v;
+      named_bar_sync(1, 128 * EH);
 #pragma unroll
       for (int gg = 0; gg < G; ++gg) {
         if (gg == g && seg_id[gg] >= 0) {
+          const bool clamp = args.p_clamp != nullptr && __ldg(args.p_clamp + p);
           float acc = 0.f;
-          for (int r = s_lo[gg]; r < s_hi[gg]; ++r) acc += srm[par * kMTile + r];
+          for (int r = s_lo[gg]; r < s_hi[gg]; ++r) {
+            float x = ex[r];
+            if (EH == 2) x = fmaxf(x, ex[kMTile + r]);
+            if (clamp) x = fmaxf(x, 0.f);
+            if (round_ref) x = round_to_input_dtype(x, is_bf16);
+            acc += x;
+          }
           if (round_sum) acc = round_to_input_dtype(acc, is_bf16);
           args.out[(int64_t)seg_id[gg] * args.ld_out + p] = acc;
         }
@@ -243,7 +264,6 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     };
 
     if (pa < pb) {
-      // leading empty pages (and the all-empty corner case) produce -inf / clamped rows
       int64_t p = pa;                                   // current page
       int64_t pend = __ldg(args.p_offsets + p + 1);     // its end row (global)
       uint32_t use = 0;
@@ -257,15 +277,22 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             mbar_wait(acc_full + a, (use / NACC) & 1u);
             tc_fence_after();
             ++use;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * NT;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * NT + c_lo * 32;
             int64_t pp = p, ppend = pend;   // rewind the page cursor for every M tile
             float m = rm[g];
             bool live = pp < pb;
-#pragma unroll 1
-            for (int c = 0; c < NT / 32; ++c) {
-              uint32_t v[32];
-              tmem_ld32(taddr + c * 32, v);
-              tmem_ld_wait();
+
+            // pages that end inside columns [.., col_end) without this warp scanning them
+            auto skip_to = [&](int col_end) {
+              while (live && ppend - trow <= col_end) {
+                finish_page(g, pp, m);
+                m = -INFINITY;
+                ++pp;
+                if (pp >= pb) { live = false; break; }
+                ppend = __ldg(args.p_offsets + pp + 1);
+              }
+            };
+            auto scan_chunk = [&](const uint32_t (&v)[32], int c) {
               if (DBG) {
                 if (blockIdx.x == 0 && t == 0 && args.dbg != nullptr) {
 #pragma unroll
@@ -273,7 +300,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                     args.dbg[(int64_t)(g * kMTile + row) * NT + c * 32 + i] = __uint_as_float(v[i]);
                 }
               }
-              if (!live) continue;
+              if (!live) return;
               const int64_t cb = trow + c * 32;         // global row of this chunk's column 0
               if (ppend - cb > 32) {
                 m = max32(v, m);
@@ -293,13 +320,30 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                   if (lo >= 32) break;
                 }
               }
+            };
+
+            if (EH == 2 && half == 1) skip_to(c_lo * 32);
+            // double-buffered TMEM reads: chunk j+1 is in flight while chunk j is reduced
+            uint32_t va[32], vb[32];
+            tmem_ld32(taddr, va);
+#pragma unroll
+            for (int j = 0; j < NOWN; j += 2) {
+              tmem_ld_wait();
+              if (j + 1 < NOWN) tmem_ld32(taddr + (j + 1) * 32, vb);
+              scan_chunk(va, c_lo + j);
+              if (j + 1 < NOWN) {
+                tmem_ld_wait();
+                if (j + 2 < NOWN) tmem_ld32(taddr + (j + 2) * 32, va);
+                scan_chunk(vb, c_lo + j + 1);
+              }
             }
-            rm[g] = m;
-            p_next = pp; pend_next = ppend;
-            // release the accumulator buffer back to the MMA warp
+            // release the accumulator buffer back to the MMA warp as early as possible
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + a);
+            if (EH == 2 && half == 0) skip_to(NT);
+            rm[g] = m;
+            p_next = pp; pend_next = ppend;
           }
         }
         p = p_next; pend = pend_next;
