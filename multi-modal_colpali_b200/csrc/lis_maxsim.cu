@@ -74,19 +74,23 @@ int sm_count(int device) {
 
 // ---------------------------------------------------------------------------------------------
 constexpr int kSmemBudget = 232448;  // 227 KB opt-in maximum per CTA on sm_100
-constexpr int kSmemTail = 3072;      // barriers + row-max exchange (2288 B used)
+constexpr int kSmemTail = 3072;      // barriers (240 B) + row-max exchange (<= 2048 B)
 
 template <int NT, int G, int EH, bool DBG>
 static int launch_maxsim(const CUtensorMap& tq, const CUtensorMap& tp, const MaxSimArgs& a, int grid,
                          cudaStream_t st) {
   const int stage = NT * kDim * 2;
-  int ns = (kSmemBudget - 1024 - kSmemTail - G * kATileBytes) / stage;
+  int ns = (kSmemBudget - kSmemTail - G * kATileBytes) / stage;
   ns = std::min(ns, 8);
   if (ns < 1) {
     set_error("tile_n=%d group=%d does not fit shared memory", NT, G);
     return LIS_E_INVALID;
   }
-  const int smem = 1024 + G * kATileBytes + ns * stage + kSmemTail;
+  const int smem = G * kATileBytes + ns * stage + kSmemTail;
+  if (a.n_mt != G) {
+    set_error("internal: n_mt=%d must equal the instantiated group %d", a.n_mt, G);
+    return LIS_E_INVALID;
+  }
   auto kern = maxsim_kernel<NT, G, EH, DBG>;
   static bool configured[64] = {false};  // per template instantiation and device
   int dev = 0;
@@ -312,10 +316,8 @@ int lis_maxsim_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, cons
     a.n_mt = (int32_t)std::min<int64_t>(g, n_mtiles - mt0);
     a.round_mode = round_mode;
     a.is_bf16 = dtype == LIS_BF16;
-    // use the smallest instantiation that holds this pass (the last pass may be short)
-    int gg = a.n_mt;
-    if (nt == 256 && gg > 3) gg = 3;
-    rc = dispatch_maxsim(nt, gg, tq, tp, a, grid, st);
+    // the instantiation whose group equals this pass's tile count (the last pass may be short)
+    rc = dispatch_maxsim(nt, a.n_mt, tq, tp, a, grid, st);
     if (rc) return rc;
   }
   return LIS_OK;

@@ -64,10 +64,14 @@ __device__ __forceinline__ float max32(const uint32_t (&v)[32], float m) {
   }
   return fmax3(m0, m1, fmaxf(m2, m3));
 }
+// max over columns [lo, hi) of a 32-column chunk (hi <= lo: nothing)
 __device__ __forceinline__ float max32_masked(const uint32_t (&v)[32], float m, int lo, int hi) {
+  const uint32_t below_hi = hi >= 32 ? 0xffffffffu : (hi <= 0 ? 0u : ((1u << hi) - 1u));
+  const uint32_t below_lo = lo >= 32 ? 0xffffffffu : (lo <= 0 ? 0u : ((1u << lo) - 1u));
+  const uint32_t mask = below_hi & ~below_lo;
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
-    const float x = (i >= lo && i < hi) ? __uint_as_float(v[i]) : -INFINITY;
+    const float x = ((mask >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY;
     m = fmaxf(m, x);
   }
   return m;
@@ -93,8 +97,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   constexpr int kBStageBytes = NT * kDim * 2;
   constexpr int kBHalfBytes = NT * 128;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];  // 128-byte swizzle atoms need 1024-byte alignment
   uint8_t* smem_a = smem;                               // [G][2][128 rows x 128 B]
   uint8_t* smem_b = smem + G * kATileBytes;             // [NS][2][NT rows x 128 B]
   uint8_t* tail = smem_b + (size_t)NS * kBStageBytes;
@@ -105,7 +108,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   uint64_t* acc_empty = acc_full + 4;                        // [NACC]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
   int64_t* range = reinterpret_cast<int64_t*>(tmem_slot + 2);  // [0]=page begin [1]=page end [2]=row0
-  float* srm = reinterpret_cast<float*>(range + 4);            // [2][EH][128] row-max exchange
+  float* srm = reinterpret_cast<float*>(range + 4);            // [2][EH*128] row-max exchange
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -206,50 +209,45 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     // ===================== epilogue (warps 2 .. 2+4*EH-1) =====================
     // EH "column halves": with EH == 2 two warps share every TMEM lane quarter and each scans half
     // of the tile's columns; their partial row maxima meet in shared memory when a page ends.
+    // The M-tile loop is deliberately NOT unrolled -- the hot loop must stay inside the instruction
+    // cache -- so the G running maxima of a thread sit in a register ring that is rotated once per
+    // M tile (the current tile's value is always rm[0]); the launcher guarantees n_mt == G.
     const int quarter = warp & 3;             // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;         // 0 .. EH-1
     const int row = quarter * 32 + lane;      // query-token row inside the M tile
+    const int etid = half * kMTile + row;     // 0 .. 128*EH-1
     const int is_bf16 = args.is_bf16;
     const bool round_ref = (args.round_mode & 1) != 0;            // round the per-token max
     const bool round_sum = round_ref && (args.round_mode & 2) == 0;  // ... and the sum, unless deferred
     constexpr int NCH = NT / 32;              // 32-column chunks per tile
     constexpr int NOWN = NCH / EH;            // chunks scanned by this warp
     const int c_lo = half * NOWN;
-
-    // segment summed by this thread (half 0 only) in each resident M tile
-    int seg_id[G], s_lo[G], s_hi[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      seg_id[g] = -1; s_lo[g] = 0; s_hi[g] = 0;
-      if (g < n_mt && half == 0) {
-        const int first = __ldg(args.mt_seg + args.mt0 + g);
-        const int last = __ldg(args.mt_seg + args.mt0 + g + 1);
-        if (first + row < last) {
-          seg_id[g] = first + row;
-          s_lo[g] = __ldg(args.seg_lo + seg_id[g]) - (args.mt0 + g) * kMTile;
-          s_hi[g] = __ldg(args.seg_hi + seg_id[g]) - (args.mt0 + g) * kMTile;
-        }
-      }
-    }
-
     float rm[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) rm[g] = -INFINITY;
+    auto rotate = [&](float cur) {
+#pragma unroll
+      for (int i = 0; i + 1 < G; ++i) rm[i] = rm[i + 1];
+      rm[G - 1] = cur;
+    };
     int par = 0;
 
     // Emit one finished page for M tile g: every epilogue thread publishes its partial row max,
-    // then the segment workers combine the halves (max), clamp / round like the reference, and sum
-    // their rows in ascending row order (deterministic).
+    // then the segment workers (threads 0.. of half 0) combine the halves (max), clamp / round like
+    // the reference, and sum their rows in ascending row order (deterministic).
     auto finish_page = [&](int g, int64_t p, float v) {
       float* ex = srm + par * (EH * kMTile);
-      ex[half * kMTile + row] = v;
+      ex[etid] = v;
       named_bar_sync(1, 128 * EH);
-#pragma unroll
-      for (int gg = 0; gg < G; ++gg) {
-        if (gg == g && seg_id[gg] >= 0) {
+      if (half == 0) {
+        const int mt = args.mt0 + g;
+        const int seg = __ldg(args.mt_seg + mt) + row;
+        if (seg < __ldg(args.mt_seg + mt + 1)) {
+          const int lo = __ldg(args.seg_lo + seg) - mt * kMTile;
+          const int hi = __ldg(args.seg_hi + seg) - mt * kMTile;
           const bool clamp = args.p_clamp != nullptr && __ldg(args.p_clamp + p);
           float acc = 0.f;
-          for (int r = s_lo[gg]; r < s_hi[gg]; ++r) {
+          for (int r = lo; r < hi; ++r) {
             float x = ex[r];
             if (EH == 2) x = fmaxf(x, ex[kMTile + r]);
             if (clamp) x = fmaxf(x, 0.f);
@@ -257,7 +255,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             acc += x;
           }
           if (round_sum) acc = round_to_input_dtype(acc, is_bf16);
-          args.out[(int64_t)seg_id[gg] * args.ld_out + p] = acc;
+          args.out[(int64_t)seg * args.ld_out + p] = acc;
         }
       }
       par ^= 1;
@@ -270,89 +268,98 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       for (int t = 0; t < ntiles; ++t) {
         const int64_t trow = row0 + (int64_t)t * NT;    // global row of column 0
         int64_t p_next = p, pend_next = pend;
-#pragma unroll
+#pragma unroll 1
         for (int g = 0; g < G; ++g) {
-          if (g < n_mt) {
-            const uint32_t a = use % NACC;
-            mbar_wait(acc_full + a, (use / NACC) & 1u);
-            tc_fence_after();
-            ++use;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * NT + c_lo * 32;
-            int64_t pp = p, ppend = pend;   // rewind the page cursor for every M tile
-            float m = rm[g];
-            bool live = pp < pb;
+          const uint32_t a = use % NACC;
+          mbar_wait(acc_full + a, (use / NACC) & 1u);
+          tc_fence_after();
+          ++use;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * NT + c_lo * 32;
+          int64_t pp = p;                   // rewind the page cursor for every M tile
+          bool live = pp < pb;
+          // end column of the current page relative to this tile (saturated; > NT: page continues)
+          auto rel_end = [&](int64_t e) { const int64_t d = e - trow; return d > NT ? NT + 1 : (int)d; };
+          int pe = rel_end(pend);
+          float m = rm[0];
 
-            // pages that end inside columns [.., col_end) without this warp scanning them
-            auto skip_to = [&](int col_end) {
-              while (live && ppend - trow <= col_end) {
-                finish_page(g, pp, m);
-                m = -INFINITY;
-                ++pp;
-                if (pp >= pb) { live = false; break; }
-                ppend = __ldg(args.p_offsets + pp + 1);
-              }
-            };
-            auto scan_chunk = [&](const uint32_t (&v)[32], int c) {
-              if (DBG) {
-                if (blockIdx.x == 0 && t == 0 && args.dbg != nullptr) {
-#pragma unroll
-                  for (int i = 0; i < 32; ++i)
-                    args.dbg[(int64_t)(g * kMTile + row) * NT + c * 32 + i] = __uint_as_float(v[i]);
-                }
-              }
-              if (!live) return;
-              const int64_t cb = trow + c * 32;         // global row of this chunk's column 0
-              if (ppend - cb > 32) {
-                m = max32(v, m);
-              } else {
-                int lo = 0;
-                while (true) {
-                  const int64_t rel = ppend - cb;
-                  const int hi = rel < 32 ? (int)rel : 32;
-                  m = max32_masked(v, m, lo, hi);
-                  if (rel > 32) break;
-                  finish_page(g, pp, m);
-                  m = -INFINITY;
-                  ++pp;
-                  if (pp >= pb) { live = false; break; }
-                  ppend = __ldg(args.p_offsets + pp + 1);
-                  lo = hi;
-                  if (lo >= 32) break;
-                }
-              }
-            };
+          auto next_page = [&]() {          // after a finish: advance the cursor
+            m = -INFINITY;
+            ++pp;
+            if (pp >= pb) { live = false; pe = NT + 1; return; }
+            pe = rel_end(__ldg(args.p_offsets + pp + 1));
+          };
+          // pages that end at or before column col_end without this warp scanning them
+          auto skip_to = [&](int col_end) {
+            while (live && pe <= col_end) { finish_page(g, pp, m); next_page(); }
+          };
 
-            if (EH == 2 && half == 1) skip_to(c_lo * 32);
+          if (EH == 2 && half == 1) skip_to(c_lo * 32);
+          if (!DBG && (!live || pe > (c_lo + NOWN) * 32)) {
+            // ---- fast path: no page ends inside this warp's columns ----
             // double-buffered TMEM reads: chunk j+1 is in flight while chunk j is reduced
             uint32_t va[32], vb[32];
             tmem_ld32(taddr, va);
 #pragma unroll
             for (int j = 0; j < NOWN; j += 2) {
               tmem_ld_wait();
-              if (j + 1 < NOWN) tmem_ld32(taddr + (j + 1) * 32, vb);
-              scan_chunk(va, c_lo + j);
-              if (j + 1 < NOWN) {
-                tmem_ld_wait();
-                if (j + 2 < NOWN) tmem_ld32(taddr + (j + 2) * 32, va);
-                scan_chunk(vb, c_lo + j + 1);
+              tmem_ld32(taddr + (j + 1) * 32, vb);
+              m = max32(va, m);
+              tmem_ld_wait();
+              if (j + 2 < NOWN) tmem_ld32(taddr + (j + 2) * 32, va);
+              m = max32(vb, m);
+            }
+          } else {
+            // ---- general path: page boundaries inside the columns (kept compact, not unrolled) ----
+#pragma unroll 1
+            for (int j = 0; j < NOWN; ++j) {
+              uint32_t v[32];
+              tmem_ld32(taddr + j * 32, v);
+              tmem_ld_wait();
+              const int cb = (c_lo + j) * 32;           // first column of this chunk
+              if (DBG) {
+                if (blockIdx.x == 0 && t == 0 && args.dbg != nullptr) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    args.dbg[(int64_t)(g * kMTile + row) * NT + cb + i] = __uint_as_float(v[i]);
+                }
+              }
+              if (!live) continue;
+              if (pe - cb > 32) {
+                m = max32(v, m);
+              } else {
+                int lo = 0;
+                while (true) {
+                  const int rel = pe - cb;
+                  const int hi = rel < 32 ? rel : 32;
+                  m = max32_masked(v, m, lo, hi);
+                  if (rel > 32) break;
+                  finish_page(g, pp, m);
+                  next_page();
+                  if (!live) break;
+                  lo = hi;
+                  if (lo >= 32) break;
+                }
               }
             }
-            // release the accumulator buffer back to the MMA warp as early as possible
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + a);
-            if (EH == 2 && half == 0) skip_to(NT);
-            rm[g] = m;
-            p_next = pp; pend_next = ppend;
           }
+          // release the accumulator buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + a);
+          if (EH == 2 && half == 0) skip_to(NT);
+          rotate(m);
+          p_next = pp;
+          pend_next = live ? __ldg(args.p_offsets + pp + 1) : pend;
         }
         p = p_next; pend = pend_next;
       }
       // pages not closed by any tile: trailing empty pages (or ntiles == 0)
       while (p < pb) {
-#pragma unroll
-        for (int g = 0; g < G; ++g)
-          if (g < n_mt) { finish_page(g, p, rm[g]); rm[g] = -INFINITY; }
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) {
+          finish_page(g, p, rm[0]);
+          rotate(-INFINITY);
+        }
         ++p;
       }
     }
