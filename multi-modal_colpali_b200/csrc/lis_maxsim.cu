@@ -248,27 +248,20 @@ static int current_device_sm_count() {
   return sm_count(dev);
 }
 
-// Tiling policy.  The op's arithmetic intensity is (query rows) FLOP per page byte, so:
-//   <= 3 M tiles: NT=256 tiles, all M tiles resident (HBM-bound up to ~2 tiles);
-//   more: NT=128 with up to 5 resident M tiles per pass over the page store.
+// Tiling policy (measured on B200, profiles/sweep_r1_*.jsonl).  The op's arithmetic intensity is
+// (query rows) FLOP per page byte.  NT = 256 wins in both regimes: HBM-bound passes want 64 KB TMA
+// tiles in flight, and tensor-bound passes read 96 B/cycle of operands from shared memory per MMA
+// instead of the 128 B/cycle (the whole smem bandwidth) that N = 128 needs.  Up to 3 query M tiles
+// stay resident (A 96 KB + 2 B stages of 64 KB); more tiles -> several passes, balanced (5 -> 3+2).
 static void choose_tiling(int64_t n_mtiles, int* nt, int* g) {
-  if (g_tuning.tile_n && g_tuning.group) {
-    *nt = g_tuning.tile_n;
-    *g = g_tuning.group;
+  *nt = g_tuning.tile_n ? g_tuning.tile_n : 256;
+  const int gmax = (*nt == 256) ? 3 : 5;
+  if (g_tuning.group) {
+    *g = std::min(g_tuning.group, gmax);
     return;
   }
-  if (n_mtiles <= 3) {
-    *nt = g_tuning.tile_n ? g_tuning.tile_n : 256;
-    *g = (int)n_mtiles;
-  } else {
-    *nt = g_tuning.tile_n ? g_tuning.tile_n : 128;
-    const int gmax = (*nt == 256) ? 3 : 5;
-    // balance the passes: e.g. 6 tiles -> 3+3 rather than 5+1
-    const int64_t passes = (n_mtiles + gmax - 1) / gmax;
-    *g = (int)((n_mtiles + passes - 1) / passes);
-  }
-  if (g_tuning.group) *g = g_tuning.group;
-  if (*nt == 256 && *g > 3) *g = 3;
+  const int64_t passes = (n_mtiles + gmax - 1) / gmax;
+  *g = (int)((n_mtiles + passes - 1) / passes);
 }
 
 int lis_maxsim_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, const int32_t* seg_hi,

@@ -265,8 +265,12 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       int64_t p = pa;                                   // current page
       int64_t pend = __ldg(args.p_offsets + p + 1);     // its end row (global)
       uint32_t use = 0;
+      constexpr int GRP = NOWN < 4 ? NOWN : 4;          // chunks held in registers at once
       for (int t = 0; t < ntiles; ++t) {
         const int64_t trow = row0 + (int64_t)t * NT;    // global row of column 0
+        // end column of a page relative to this tile (saturated; > NT: the page continues)
+        auto rel_end = [&](int64_t e) { const int64_t d = e - trow; return d > NT ? NT + 1 : (int)d; };
+        const int pe_tile = rel_end(pend);
         int64_t p_next = p, pend_next = pend;
 #pragma unroll 1
         for (int g = 0; g < G; ++g) {
@@ -275,81 +279,85 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           tc_fence_after();
           ++use;
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * NT + c_lo * 32;
-          int64_t pp = p;                   // rewind the page cursor for every M tile
+          int64_t pp = p, ppend = pend;     // rewind the page cursor for every M tile
           bool live = pp < pb;
-          // end column of the current page relative to this tile (saturated; > NT: page continues)
-          auto rel_end = [&](int64_t e) { const int64_t d = e - trow; return d > NT ? NT + 1 : (int)d; };
-          int pe = rel_end(pend);
+          int pe = pe_tile;
           float m = rm[0];
 
           auto next_page = [&]() {          // after a finish: advance the cursor
             m = -INFINITY;
             ++pp;
             if (pp >= pb) { live = false; pe = NT + 1; return; }
-            pe = rel_end(__ldg(args.p_offsets + pp + 1));
+            ppend = __ldg(args.p_offsets + pp + 1);
+            pe = rel_end(ppend);
           };
           // pages that end at or before column col_end without this warp scanning them
           auto skip_to = [&](int col_end) {
             while (live && pe <= col_end) { finish_page(g, pp, m); next_page(); }
           };
-
-          if (EH == 2 && half == 1) skip_to(c_lo * 32);
-          if (!DBG && (!live || pe > (c_lo + NOWN) * 32)) {
-            // ---- fast path: no page ends inside this warp's columns ----
-            // double-buffered TMEM reads: chunk j+1 is in flight while chunk j is reduced
-            uint32_t va[32], vb[32];
-            tmem_ld32(taddr, va);
+          // one 32-column chunk starting at tile column cb
+          auto scan = [&](const uint32_t (&v)[32], int cb) {
+            if (DBG) {
+              if (blockIdx.x == 0 && t == 0 && args.dbg != nullptr) {
 #pragma unroll
-            for (int j = 0; j < NOWN; j += 2) {
-              tmem_ld_wait();
-              tmem_ld32(taddr + (j + 1) * 32, vb);
-              m = max32(va, m);
-              tmem_ld_wait();
-              if (j + 2 < NOWN) tmem_ld32(taddr + (j + 2) * 32, va);
-              m = max32(vb, m);
+                for (int i = 0; i < 32; ++i)
+                  args.dbg[(int64_t)(g * kMTile + row) * NT + cb + i] = __uint_as_float(v[i]);
+              }
             }
-          } else {
-            // ---- general path: page boundaries inside the columns (kept compact, not unrolled) ----
-#pragma unroll 1
-            for (int j = 0; j < NOWN; ++j) {
-              uint32_t v[32];
-              tmem_ld32(taddr + j * 32, v);
-              tmem_ld_wait();
-              const int cb = (c_lo + j) * 32;           // first column of this chunk
-              if (DBG) {
-                if (blockIdx.x == 0 && t == 0 && args.dbg != nullptr) {
+            if (!live) return;
+            if (pe - cb > 32) { m = max32(v, m); return; }
+            int lo = 0;
+            while (true) {
+              const int rel = pe - cb;
+              const int hi = rel < 32 ? rel : 32;
+              m = max32_masked(v, m, lo, hi);
+              if (rel > 32) break;
+              finish_page(g, pp, m);
+              next_page();
+              if (!live) break;
+              lo = hi;
+              if (lo >= 32) break;
+            }
+          };
+
+          // The accumulator buffer is the scarce resource (512/NT of them feed the tensor pipe):
+          // pull this warp's columns into registers with all loads in flight, hand the buffer
+          // straight back to the MMA warp, and only then do the arithmetic and the page logic.
 #pragma unroll
-                  for (int i = 0; i < 32; ++i)
-                    args.dbg[(int64_t)(g * kMTile + row) * NT + cb + i] = __uint_as_float(v[i]);
-                }
+          for (int grp = 0; grp < NOWN / GRP; ++grp) {
+            uint32_t v0[32], v1[32], v2[32], v3[32];
+            const uint32_t ta = taddr + grp * GRP * 32;
+            tmem_ld32(ta, v0);
+            if (GRP > 1) tmem_ld32(ta + 32, v1);
+            if (GRP > 2) tmem_ld32(ta + 64, v2);
+            if (GRP > 3) tmem_ld32(ta + 96, v3);
+            tmem_ld_wait();
+            if (grp == NOWN / GRP - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(acc_empty + a);
+            }
+            const int cb = (c_lo + grp * GRP) * 32;
+            if (grp == 0 && EH == 2 && half == 1) skip_to(c_lo * 32);
+            if (!DBG && (!live || pe > cb + GRP * 32)) {
+              // fast path: no page ends inside these columns
+              if (live) {
+                m = max32(v0, m);
+                if (GRP > 1) m = max32(v1, m);
+                if (GRP > 2) m = max32(v2, m);
+                if (GRP > 3) m = max32(v3, m);
               }
-              if (!live) continue;
-              if (pe - cb > 32) {
-                m = max32(v, m);
-              } else {
-                int lo = 0;
-                while (true) {
-                  const int rel = pe - cb;
-                  const int hi = rel < 32 ? rel : 32;
-                  m = max32_masked(v, m, lo, hi);
-                  if (rel > 32) break;
-                  finish_page(g, pp, m);
-                  next_page();
-                  if (!live) break;
-                  lo = hi;
-                  if (lo >= 32) break;
-                }
-              }
+            } else {
+              scan(v0, cb);
+              if (GRP > 1) scan(v1, cb + 32);
+              if (GRP > 2) scan(v2, cb + 64);
+              if (GRP > 3) scan(v3, cb + 96);
             }
           }
-          // release the accumulator buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty + a);
           if (EH == 2 && half == 0) skip_to(NT);
           rotate(m);
           p_next = pp;
-          pend_next = live ? __ldg(args.p_offsets + pp + 1) : pend;
+          pend_next = ppend;
         }
         p = p_next; pend = pend_next;
       }

@@ -67,13 +67,14 @@ def report(name, nq, qtok, pages, ptok, tilings, ragged=None):
 which = sys.argv[1:] or ["c2", "hbm", "c5", "c3"]
 if "c2" in which:
     report("c2_32x20_vs_100kx1030", 32, 20, 100_000, 1030,
-           [(0, 0), (128, 5, 1), (128, 5, 2), (128, 3, 1), (128, 3, 2), (256, 3, 1), (256, 3, 2), (128, 1, 2), (256, 1, 2)])
+           [(0, 0), (256, 3, 2), (256, 3, 1), (128, 5, 2), (256, 2, 2), (256, 1, 2), (0, 0)])
 if "hbm" in which:
-    report("single_query_16tok_vs_100kx1030", 1, 16, 100_000, 1030, [(0, 0), (256, 1, 1), (256, 1, 2), (128, 1, 1), (128, 1, 2)])
+    report("single_query_16tok_vs_100kx1030", 1, 16, 100_000, 1030, [(0, 0), (256, 1, 1), (256, 1, 2), (128, 1, 2)])
     report("4q_32tok_vs_100kx1030", 4, 32, 100_000, 1030, [(0, 0), (256, 1, 1), (256, 1, 2)])
-    report("8q_32tok_vs_100kx1030", 8, 32, 100_000, 1030, [(0, 0), (256, 2, 1), (256, 2, 2), (128, 2, 2)])
+    report("8q_32tok_vs_100kx1030", 8, 32, 100_000, 1030, [(0, 0), (256, 2, 1), (256, 2, 2)])
 if "c5" in which:
-    report("c5_slice_1024x32_vs_20kx1030", 1024, 32, 20_000, 1030, [(0, 0), (128, 4, 1), (128, 4, 2), (128, 5, 2), (256, 3, 1), (256, 3, 2)])
+    report("c5_slice_1024x32_vs_20kx1030", 1024, 32, 20_000, 1030, [(0, 0), (256, 3, 2), (256, 3, 1), (128, 5, 2), (128, 4, 2)])
 if "c3" in which:
     lens = torch.randint(256, 769, (200_000,), generator=torch.Generator().manual_seed(3003)).tolist()
     report("c3_slice_1q32_vs_200k_ragged256-768", 1, 32, 200_000, 0, [(0, 0), (256, 1, 1)], ragged=lens)
+    report("c3_slice_32q32_vs_200k_ragged256-768", 32, 32, 200_000, 0, [(0, 0)], ragged=lens)
