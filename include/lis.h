@@ -105,17 +105,21 @@ int lis_maxsim_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, cons
 int lis_reduce_segments(const float* seg_scores, int64_t ld_seg, const int32_t* seg_first, int64_t nq,
                         int64_t np, int round_mode, int dtype, float* out, int64_t ld_out, void* stream);
 
-/* Tuning / debug knobs (process-wide).  tile_n in {0 (auto), 128, 256}: page-token rows per MMA tile;
- * group in {0 (auto), 1..5}: query M tiles resident per pass; max_ctas 0 = one per SM; epi_halves in
- * {0 (auto), 1, 2}: 4 or 8 epilogue warps.  Used by sweeps and tests; the defaults are what ships. */
-int lis_set_tuning(int tile_n, int group, int max_ctas, int epi_halves);
+/* Tuning / debug knobs (process-wide); 0 always means "auto", and the defaults are what ships.
+ *   tile_n     {0, 128, 192, 256}  page-token rows per MMA tile
+ *   group      {0, 1..5}           query M tiles resident per pass over the page store
+ *   max_ctas   0 = one per SM
+ *   epi_halves {0, 1, 2}           4 or 8 epilogue warps
+ *   a_operand  {0, 1, 2}           query operand of the MMA in shared memory (1) or tensor memory (2) */
+int lis_set_tuning(int tile_n, int group, int max_ctas, int epi_halves, int a_operand);
 /* Number of kernels this library launched since load (all entry points). */
 int64_t lis_launch_count(void);
 
 /* Debug: raw similarities of M tile 0 against the first `tile_n` token rows, out[128, tile_n]
- * (device float), straight from TMEM.  Exercises the exact TMA/UMMA path of lis_maxsim_scores. */
+ * (device float), straight from TMEM.  Exercises the exact TMA/UMMA path of lis_maxsim_scores
+ * (a_in_tmem selects the TS form). */
 int lis_debug_sim_tile(const void* q, int64_t q_rows, const void* tokens, int64_t n_rows, int dtype,
-                       int tile_n, float* out, void* stream);
+                       int tile_n, int a_in_tmem, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K2: per-query top-k over a score matrix, deterministic order (score desc, id asc).

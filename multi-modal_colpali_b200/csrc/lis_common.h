@@ -21,6 +21,7 @@ struct Tuning {
   int group = 0;
   int max_ctas = 0;
   int epi_halves = 0;  // 0 = auto
+  int a_operand = 0;   // 0 = auto, 1 = shared memory (SS), 2 = tensor memory (TS)
 };
 extern Tuning g_tuning;
 

@@ -76,22 +76,23 @@ int sm_count(int device) {
 constexpr int kSmemBudget = 232448;  // 227 KB opt-in maximum per CTA on sm_100
 constexpr int kSmemTail = 3072;      // barriers (240 B) + row-max exchange (<= 2048 B)
 
-template <int NT, int G, int EH, bool DBG>
+template <int NT, int G, int EH, bool ATM, bool DBG>
 static int launch_maxsim(const CUtensorMap& tq, const CUtensorMap& tp, const MaxSimArgs& a, int grid,
                          cudaStream_t st) {
   const int stage = NT * kDim * 2;
-  int ns = (kSmemBudget - kSmemTail - G * kATileBytes) / stage;
+  const int a_bytes = ATM ? 0 : G * kATileBytes;
+  int ns = (kSmemBudget - kSmemTail - a_bytes) / stage;
   ns = std::min(ns, 8);
   if (ns < 1) {
     set_error("tile_n=%d group=%d does not fit shared memory", NT, G);
     return LIS_E_INVALID;
   }
-  const int smem = G * kATileBytes + ns * stage + kSmemTail;
+  const int smem = a_bytes + ns * stage + kSmemTail;
   if (a.n_mt != G) {
     set_error("internal: n_mt=%d must equal the instantiated group %d", a.n_mt, G);
     return LIS_E_INVALID;
   }
-  auto kern = maxsim_kernel<NT, G, EH, DBG>;
+  auto kern = maxsim_kernel<NT, G, EH, ATM, DBG>;
   static bool configured[64] = {false};  // per template instantiation and device
   int dev = 0;
   LIS_CUDA_CHECK(cudaGetDevice(&dev));
@@ -105,22 +106,34 @@ static int launch_maxsim(const CUtensorMap& tq, const CUtensorMap& tp, const Max
   return LIS_OK;
 }
 
-static int dispatch_maxsim(int nt, int g, const CUtensorMap& tq, const CUtensorMap& tp, const MaxSimArgs& a,
-                           int grid, cudaStream_t st, bool dbg = false) {
+// Instantiations.  SS form (A in shared memory): NT 256 x G 1..3, NT 128 x G 1..5.
+// TS form (A in tensor memory): 64*G + NACC*NT <= 512 columns -> NT 128 x G 1..4, NT 192 x G 1..2.
+static int dispatch_maxsim(int nt, int g, bool atm, const CUtensorMap& tq, const CUtensorMap& tp,
+                           const MaxSimArgs& a, int grid, cudaStream_t st, bool dbg = false) {
   if (dbg) {
-    if (nt == 256 && g == 1) return launch_maxsim<256, 1, 2, true>(tq, tp, a, grid, st);
-    if (nt == 128 && g == 1) return launch_maxsim<128, 1, 1, true>(tq, tp, a, grid, st);
+    if (nt == 256 && g == 1 && !atm) return launch_maxsim<256, 1, 2, false, true>(tq, tp, a, grid, st);
+    if (nt == 128 && g == 1 && !atm) return launch_maxsim<128, 1, 1, false, true>(tq, tp, a, grid, st);
+    if (nt == 128 && g == 1 && atm) return launch_maxsim<128, 1, 2, true, true>(tq, tp, a, grid, st);
+    if (nt == 192 && g == 1 && atm) return launch_maxsim<192, 1, 2, true, true>(tq, tp, a, grid, st);
   }
   const int eh = g_tuning.epi_halves ? g_tuning.epi_halves : 2;
-#define LIS_CASE(NT_, G_)                                                                   \
-  if (nt == NT_ && g == G_)                                                                 \
-    return eh == 2 ? launch_maxsim<NT_, G_, 2, false>(tq, tp, a, grid, st)                  \
-                   : launch_maxsim<NT_, G_, 1, false>(tq, tp, a, grid, st);
-  LIS_CASE(256, 1) LIS_CASE(256, 2) LIS_CASE(256, 3)
-  LIS_CASE(128, 1) LIS_CASE(128, 2) LIS_CASE(128, 3) LIS_CASE(128, 4) LIS_CASE(128, 5)
+#define LIS_CASE(NT_, G_, ATM_)                                                                \
+  if (nt == NT_ && g == G_ && atm == ATM_)                                                     \
+    return eh == 2 ? launch_maxsim<NT_, G_, 2, ATM_, false>(tq, tp, a, grid, st)               \
+                   : launch_maxsim<NT_, G_, 1, ATM_, false>(tq, tp, a, grid, st);
+  LIS_CASE(256, 1, false) LIS_CASE(256, 2, false) LIS_CASE(256, 3, false)
+  LIS_CASE(128, 1, false) LIS_CASE(128, 2, false) LIS_CASE(128, 3, false) LIS_CASE(128, 4, false)
+  LIS_CASE(128, 5, false)
+  LIS_CASE(128, 1, true) LIS_CASE(128, 2, true) LIS_CASE(128, 3, true) LIS_CASE(128, 4, true)
+  LIS_CASE(192, 1, true) LIS_CASE(192, 2, true)
 #undef LIS_CASE
-  set_error("unsupported tiling tile_n=%d group=%d", nt, g);
+  set_error("unsupported tiling tile_n=%d group=%d a_in_tmem=%d", nt, g, (int)atm);
   return LIS_E_INVALID;
+}
+
+static int max_group(int nt, bool atm) {
+  if (atm) return nt == 128 ? 4 : (nt == 192 ? 2 : 0);
+  return nt == 256 ? 3 : (nt == 128 ? 5 : 0);
 }
 
 }  // namespace lis
@@ -143,17 +156,23 @@ int lis_device_supported(int device) {
   return LIS_OK;
 }
 
-int lis_set_tuning(int tile_n, int group, int max_ctas, int epi_halves) {
-  const int epi = epi_halves;
-  LIS_REQUIRE(epi >= 0 && epi <= 2, "epi_halves must be 0 (auto), 1 or 2");
-  LIS_REQUIRE(tile_n == 0 || tile_n == 128 || tile_n == 256, "tile_n must be 0, 128 or 256");
-  LIS_REQUIRE(group >= 0 && group <= 5, "group must be in 0..5");
-  LIS_REQUIRE(!(tile_n == 256 && group > 3), "tile_n=256 supports group <= 3");
+int lis_set_tuning(int tile_n, int group, int max_ctas, int epi_halves, int a_operand) {
+  LIS_REQUIRE(tile_n == 0 || tile_n == 128 || tile_n == 192 || tile_n == 256, "tile_n must be 0, 128, 192 or 256");
+  LIS_REQUIRE(a_operand >= 0 && a_operand <= 2, "a_operand must be 0 (auto), 1 (shared memory) or 2 (tensor memory)");
+  LIS_REQUIRE(epi_halves >= 0 && epi_halves <= 2, "epi_halves must be 0 (auto), 1 or 2");
   LIS_REQUIRE(max_ctas >= 0, "max_ctas must be >= 0");
+  LIS_REQUIRE(group >= 0 && group <= 5, "group must be in 0..5");
+  if (tile_n && a_operand) {
+    const int gm = max_group(tile_n, a_operand == 2);
+    LIS_REQUIRE(gm > 0, "tile_n=%d is not available with a_operand=%d", tile_n, a_operand);
+    LIS_REQUIRE(group <= gm, "tile_n=%d a_operand=%d supports group <= %d", tile_n, a_operand, gm);
+  }
+  LIS_REQUIRE(!(tile_n == 256 && group > 3), "tile_n=256 supports group <= 3");
   g_tuning.tile_n = tile_n;
   g_tuning.group = group;
   g_tuning.max_ctas = max_ctas;
-  g_tuning.epi_halves = epi;
+  g_tuning.epi_halves = epi_halves;
+  g_tuning.a_operand = a_operand;
   return LIS_OK;
 }
 
@@ -248,14 +267,22 @@ static int current_device_sm_count() {
   return sm_count(dev);
 }
 
-// Tiling policy (measured on B200, profiles/sweep_r1_*.jsonl).  The op's arithmetic intensity is
-// (query rows) FLOP per page byte.  NT = 256 wins in both regimes: HBM-bound passes want 64 KB TMA
-// tiles in flight, and tensor-bound passes read 96 B/cycle of operands from shared memory per MMA
-// instead of the 128 B/cycle (the whole smem bandwidth) that N = 128 needs.  Up to 3 query M tiles
-// stay resident (A 96 KB + 2 B stages of 64 KB); more tiles -> several passes, balanced (5 -> 3+2).
-static void choose_tiling(int64_t n_mtiles, int* nt, int* g) {
-  *nt = g_tuning.tile_n ? g_tuning.tile_n : 256;
-  const int gmax = (*nt == 256) ? 3 : 5;
+// Tiling policy (measured on B200, profiles/).  The op's arithmetic intensity is (query rows) FLOP per
+// page byte, so up to 2 query M tiles the pass is HBM-bound and beyond that tensor-bound.
+//  * <= 2 M tiles: SS form, NT = 256 (64 KB TMA tiles keep enough bytes in flight for HBM).
+//  * more: TS form (queries in tensor memory), NT = 128, up to 4 resident M tiles per pass, passes
+//    balanced (5 -> 3+2).  The SS form tops out at ~73 % tensor-pipe activity because its operand
+//    reads saturate shared memory (profiles/README_r1.md).
+static void choose_tiling(int64_t n_mtiles, int* nt, int* g, bool* atm) {
+  if (g_tuning.a_operand) *atm = g_tuning.a_operand == 2;
+  else *atm = n_mtiles > 2;
+  if (g_tuning.tile_n) *nt = g_tuning.tile_n;
+  else *nt = *atm ? 128 : 256;
+  int gmax = max_group(*nt, *atm);
+  if (gmax == 0) {  // inconsistent override: fall back to the default tile for this form
+    *nt = *atm ? 128 : 256;
+    gmax = max_group(*nt, *atm);
+  }
   if (g_tuning.group) {
     *g = std::min(g_tuning.group, gmax);
     return;
@@ -285,7 +312,8 @@ int lis_maxsim_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, cons
   int rc = encode_rows_tmap(&tq, q, q_rows, kMTile, dtype);
   if (rc) return rc;
   int nt, g;
-  choose_tiling(n_mtiles, &nt, &g);
+  bool atm;
+  choose_tiling(n_mtiles, &nt, &g, &atm);
   // an empty token store still needs a valid map: point it at the query rows (never loaded)
   rc = n_rows > 0 ? encode_rows_tmap(&tp, tokens, n_rows, nt, dtype) : encode_rows_tmap(&tp, q, q_rows, nt, dtype);
   if (rc) return rc;
@@ -303,6 +331,8 @@ int lis_maxsim_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, cons
     a.mt_seg = mt_seg;
     a.out = out;
     a.dbg = nullptr;
+    a.q = q;
+    a.q_rows = q_rows;
     a.ld_out = ld_out;
     a.np = np;
     a.mt0 = (int32_t)mt0;
@@ -310,7 +340,7 @@ int lis_maxsim_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, cons
     a.round_mode = round_mode;
     a.is_bf16 = dtype == LIS_BF16;
     // the instantiation whose group equals this pass's tile count (the last pass may be short)
-    rc = dispatch_maxsim(nt, a.n_mt, tq, tp, a, grid, st);
+    rc = dispatch_maxsim(nt, a.n_mt, atm, tq, tp, a, grid, st);
     if (rc) return rc;
   }
   return LIS_OK;
@@ -326,9 +356,10 @@ __global__ void fill_iota_offsets(int64_t* off, int32_t* seg_lo, int32_t* seg_hi
 }  // namespace
 
 int lis_debug_sim_tile(const void* q, int64_t q_rows, const void* tokens, int64_t n_rows, int dtype,
-                       int tile_n, float* out, void* stream) {
+                       int tile_n, int a_in_tmem, float* out, void* stream) {
   LIS_REQUIRE(q && tokens && out, "lis_debug_sim_tile: null pointer");
-  LIS_REQUIRE(tile_n == 128 || tile_n == 256, "tile_n must be 128 or 256");
+  LIS_REQUIRE(a_in_tmem ? (tile_n == 128 || tile_n == 192) : (tile_n == 128 || tile_n == 256),
+              "tile_n must be 128/256 (shared-memory A) or 128/192 (tensor-memory A)");
   LIS_REQUIRE(q_rows > 0 && n_rows > 0, "empty input");
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap tq, tp;
@@ -350,7 +381,9 @@ int lis_debug_sim_tile(const void* q, int64_t q_rows, const void* tokens, int64_
   a.p_offsets = off; a.p_clamp = nullptr; a.seg_lo = seg_lo; a.seg_hi = seg_hi; a.mt_seg = mt_seg;
   a.out = dummy; a.dbg = out; a.ld_out = 1; a.np = 1; a.mt0 = 0; a.n_mt = 1; a.round_mode = 0;
   a.is_bf16 = dtype == LIS_BF16;
-  rc = dispatch_maxsim(tile_n, 1, tq, tp, a, 1, st, true);
+  a.q = q;
+  a.q_rows = q_rows;
+  rc = dispatch_maxsim(tile_n, 1, a_in_tmem != 0, tq, tp, a, 1, st, true);
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(scratch);
   if (rc) return rc;

@@ -39,6 +39,8 @@ struct MaxSimArgs {
   const int32_t* mt_seg;     // [n_mtiles_total+1]
   float* out;                // [n_seg, ld_out]
   float* dbg;                // debug: raw sims of (tile 0 of CTA 0), [G*128, NT]; normally null
+  const void* q;             // [q_rows, 128] packed query rows (read directly by the A-in-TMEM form)
+  int64_t q_rows;
   int64_t ld_out;
   int64_t np;
   int32_t mt0;        // first M tile of this launch
@@ -87,19 +89,26 @@ __device__ __forceinline__ int64_t lower_bound_off(const int64_t* off, int64_t n
   return lo;
 }
 
-template <int NT, int G, int EH, bool DBG>
+// ATM ("A in tensor memory"): the query M tiles are stored in TMEM (64 columns each, two 16-bit
+// values per 32-bit cell) and the MMA takes its A operand from there (TS form).  Shared memory then
+// serves only the page tiles: the SS form at M=128 x N=256 reads 96 B/clk of operands from smem,
+// which is the measured operand-fetch limit (profiles/micro_mma_rate_r1.txt), so every TMA write
+// competes with the tensor pipe; with A in TMEM the MMA reads 64 B/clk at any N.
+template <int NT, int G, int EH, bool ATM, bool DBG>
 __global__ void __launch_bounds__(64 + 128 * EH, 1)
 maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_p,
               const MaxSimArgs args, const int NS) {
-  static_assert(NT == 128 || NT == 256, "tile_n");
+  static_assert(NT == 128 || NT == 192 || NT == 256, "tile_n");
   static_assert(EH == 1 || EH == 2, "epilogue halves");
-  constexpr int NACC = kTmemCols / NT;
+  constexpr int kACols = ATM ? 64 * G : 0;              // TMEM columns holding the query tiles
+  constexpr int NACC = (kTmemCols - kACols) / NT;       // accumulator buffers
+  static_assert(NACC >= 2 && NACC <= 4, "need at least two accumulator buffers");
   constexpr int kBStageBytes = NT * kDim * 2;
   constexpr int kBHalfBytes = NT * 128;
 
   extern __shared__ __align__(1024) uint8_t smem[];  // 128-byte swizzle atoms need 1024-byte alignment
-  uint8_t* smem_a = smem;                               // [G][2][128 rows x 128 B]
-  uint8_t* smem_b = smem + G * kATileBytes;             // [NS][2][NT rows x 128 B]
+  uint8_t* smem_a = smem;                               // [G][2][128 rows x 128 B] (SS form only)
+  uint8_t* smem_b = smem + (ATM ? 0 : G * kATileBytes); // [NS][2][NT rows x 128 B]
   uint8_t* tail = smem_b + (size_t)NS * kBStageBytes;
   uint64_t* q_full = reinterpret_cast<uint64_t*>(tail);      // 1
   uint64_t* b_full = q_full + 1;                             // [NS]
@@ -116,7 +125,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_p);
-    mbar_init(q_full, 1);
+    mbar_init(q_full, ATM ? 4 * EH : 1);
     for (int s = 0; s < NS; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
     for (int a = 0; a < NACC; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, 4 * EH); }
     fence_barrier_init();
@@ -157,7 +166,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0 && pa < pb) {
-      if (ntiles > 0) {
+      if (!ATM && ntiles > 0) {
         mbar_arrive_expect_tx(q_full, (uint32_t)n_mt * kATileBytes);
         for (int g = 0; g < n_mt; ++g)
           for (int h = 0; h < 2; ++h)
@@ -191,14 +200,19 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           const uint32_t a = use % NACC;
           mbar_wait(acc_empty + a, ((use / NACC) & 1u) ^ 1u);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + a * NT;
+          const uint32_t d_tmem = tmem_base + kACols + a * NT;
 #pragma unroll
           for (int k = 0; k < kDim / 16; ++k) {
             const uint32_t koff = (uint32_t)(k >> 2) * (kMTile * 128) + (uint32_t)(k & 3) * 32;
             const uint32_t koff_b = (uint32_t)(k >> 2) * kBHalfBytes + (uint32_t)(k & 3) * 32;
-            const uint64_t adesc = make_kmajor_sw128_desc(a_base + g * kATileBytes + koff);
             const uint64_t bdesc = make_kmajor_sw128_desc(b_base + s * kBStageBytes + koff_b);
-            umma_f16(d_tmem, adesc, bdesc, idesc, k > 0 ? 1u : 0u);
+            if (ATM) {
+              // 16 K-elements of a 16-bit operand = 8 TMEM columns per k-step
+              umma_f16_ts(d_tmem, tmem_base + g * 64 + k * 8, bdesc, idesc, k > 0 ? 1u : 0u);
+            } else {
+              const uint64_t adesc = make_kmajor_sw128_desc(a_base + g * kATileBytes + koff);
+              umma_f16(d_tmem, adesc, bdesc, idesc, k > 0 ? 1u : 0u);
+            }
           }
           umma_commit(acc_full + a);
         }
@@ -222,6 +236,32 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     constexpr int NCH = NT / 32;              // 32-column chunks per tile
     constexpr int NOWN = NCH / EH;            // chunks scanned by this warp
     const int c_lo = half * NOWN;
+    if (ATM && pa < pb && ntiles > 0) {
+      // Stage the query tiles in TMEM: thread = row, cell c of the row = its bytes [4c, 4c+4).
+      // Rows past the end of the query matrix are zero (they belong to no segment).
+      constexpr int kCols = 64 / EH;              // columns written by this warp per M tile
+      for (int g = 0; g < G; ++g) {
+        const int64_t qrow = (int64_t)(args.mt0 + g) * kMTile + row;
+        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(args.q) + qrow * 256 +
+                                                          half * (kCols * 4));
+#pragma unroll
+        for (int c = 0; c < kCols / 32; ++c) {
+          uint32_t v[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint4 x = make_uint4(0, 0, 0, 0);
+            if (qrow < args.q_rows) x = __ldg(src + c * 8 + i);
+            v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+          }
+          tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + g * 64 + half * kCols + c * 32, v);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_full);
+    }
+
     float rm[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) rm[g] = -INFINITY;
@@ -278,7 +318,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           mbar_wait(acc_full + a, (use / NACC) & 1u);
           tc_fence_after();
           ++use;
-          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * NT + c_lo * 32;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + kACols + a * NT + c_lo * 32;
           int64_t pp = p, ppend = pend;     // rewind the page cursor for every M tile
           bool live = pp < pb;
           int pe = pe_tile;

@@ -50,15 +50,16 @@ def report(name, nq, qtok, pages, ptok, tilings, ragged=None):
     for til in tilings:
         nt, grp = til[0], til[1]
         eh = til[2] if len(til) > 2 else 0
-        native.check(lib.lis_set_tuning(nt, grp, 0, eh))
+        aop = til[3] if len(til) > 3 else 0
+        native.check(lib.lis_set_tuning(nt, grp, 0, eh, aop))
         best, mean = time_k1(pq, store)
         rec = {"case": name, "nq": nq, "qtok": qtok, "pages": pages, "ptok": ptok, "rows": rows, "tile_n": nt,
-               "group": grp, "epi_halves": eh, "ms_best": best, "ms_mean": mean, "tflops": flops / (best * 1e-3) / 1e12,
+               "group": grp, "epi_halves": eh, "a_operand": aop, "ms_best": best, "ms_mean": mean, "tflops": flops / (best * 1e-3) / 1e12,
                "gbs": byts / (best * 1e-3) / 1e9, "pairs_per_s": nq * pages / (best * 1e-3)}
         print(json.dumps(rec), flush=True)
         out.write(json.dumps(rec) + "\n")
         out.flush()
-    lib.lis_set_tuning(0, 0, 0, 0)
+    lib.lis_set_tuning(0, 0, 0, 0, 0)
     idx.close()
     del store, idx
     torch.cuda.empty_cache()
@@ -67,14 +68,15 @@ def report(name, nq, qtok, pages, ptok, tilings, ragged=None):
 which = sys.argv[1:] or ["c2", "hbm", "c5", "c3"]
 if "c2" in which:
     report("c2_32x20_vs_100kx1030", 32, 20, 100_000, 1030,
-           [(0, 0), (256, 3, 2), (256, 3, 1), (128, 5, 2), (256, 2, 2), (256, 1, 2), (0, 0)])
+           [(0, 0), (256, 3, 2, 1), (128, 4, 2, 2), (128, 3, 2, 2), (128, 2, 2, 2), (192, 2, 2, 2), (128, 3, 1, 2), (0, 0)])
 if "hbm" in which:
-    report("single_query_16tok_vs_100kx1030", 1, 16, 100_000, 1030, [(0, 0), (256, 1, 1), (256, 1, 2), (128, 1, 2)])
-    report("4q_32tok_vs_100kx1030", 4, 32, 100_000, 1030, [(0, 0), (256, 1, 1), (256, 1, 2)])
-    report("8q_32tok_vs_100kx1030", 8, 32, 100_000, 1030, [(0, 0), (256, 2, 1), (256, 2, 2)])
+    report("single_query_16tok_vs_100kx1030", 1, 16, 100_000, 1030, [(0, 0), (256, 1, 2, 1), (128, 1, 2, 2), (192, 1, 2, 2)])
+    report("4q_32tok_vs_100kx1030", 4, 32, 100_000, 1030, [(0, 0), (256, 1, 2, 1), (192, 1, 2, 2)])
+    report("8q_32tok_vs_100kx1030", 8, 32, 100_000, 1030, [(0, 0), (256, 2, 2, 1), (192, 2, 2, 2), (128, 2, 2, 2)])
 if "c5" in which:
-    report("c5_slice_1024x32_vs_20kx1030", 1024, 32, 20_000, 1030, [(0, 0), (256, 3, 2), (256, 3, 1), (128, 5, 2), (128, 4, 2)])
+    report("c5_slice_1024x32_vs_20kx1030", 1024, 32, 20_000, 1030,
+           [(0, 0), (256, 3, 2, 1), (128, 4, 2, 2), (128, 3, 2, 2), (192, 2, 2, 2), (128, 2, 2, 2), (128, 4, 1, 2)])
 if "c3" in which:
     lens = torch.randint(256, 769, (200_000,), generator=torch.Generator().manual_seed(3003)).tolist()
-    report("c3_slice_1q32_vs_200k_ragged256-768", 1, 32, 200_000, 0, [(0, 0), (256, 1, 1)], ragged=lens)
-    report("c3_slice_32q32_vs_200k_ragged256-768", 32, 32, 200_000, 0, [(0, 0)], ragged=lens)
+    report("c3_slice_1q32_vs_200k_ragged256-768", 1, 32, 200_000, 0, [(0, 0), (256, 1, 1, 1)], ragged=lens)
+    report("c3_slice_32q32_vs_200k_ragged256-768", 32, 32, 200_000, 0, [(0, 0), (256, 3, 2, 1)], ragged=lens)

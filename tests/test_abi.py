@@ -89,9 +89,9 @@ def test_plan_queries_errors(native):
 
 def test_argument_validation_without_gpu(native):
     lib = native.load()
-    assert lib.lis_set_tuning(64, 0, 0, 0) == native.LIS_E_INVALID
-    assert lib.lis_set_tuning(256, 4, 0, 0) == native.LIS_E_INVALID
-    assert lib.lis_set_tuning(0, 0, 0, 0) == 0
+    assert lib.lis_set_tuning(64, 0, 0, 0, 0) == native.LIS_E_INVALID
+    assert lib.lis_set_tuning(256, 4, 0, 0, 0) == native.LIS_E_INVALID
+    assert lib.lis_set_tuning(0, 0, 0, 0, 0) == 0
     assert lib.lis_maxsim_scores(None, 0, None, None, None, 0, 0, None, 0, None, None, 0, 0, 0, None, 0, None) \
         == native.LIS_E_INVALID
     assert "null pointer" in native.last_error()

@@ -8,22 +8,25 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("tile_n", [128, 256])
+@pytest.mark.parametrize("tile_n,a_in_tmem", [(128, 0), (256, 0), (128, 1), (192, 1)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-def test_sim_tile_matches_matmul(lis, tile_n, dtype):
+def test_sim_tile_matches_matmul(lis, tile_n, a_in_tmem, dtype):
     from importlib import import_module
 
     N = import_module("multi-modal_colpali_b200._native")
     lib = N.load()
     g = torch.Generator().manual_seed(7)
-    q = torch.randn(128, 128, generator=g).to(dtype).cuda()
+    q = torch.randn(100, 128, generator=g).to(dtype).cuda()      # 28 rows short of a full M tile
     p = torch.randn(tile_n + 40, 128, generator=g).to(dtype).cuda()
     out = torch.full((128, tile_n), float("nan"), dtype=torch.float32, device="cuda")
-    rc = lib.lis_debug_sim_tile(q.data_ptr(), 128, p.data_ptr(), p.shape[0], 0 if dtype == torch.bfloat16 else 1,
-                                tile_n, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    rc = lib.lis_debug_sim_tile(q.data_ptr(), q.shape[0], p.data_ptr(), p.shape[0], 0 if dtype == torch.bfloat16 else 1,
+                                tile_n, a_in_tmem, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
     N.check(rc)
     torch.cuda.synchronize()
-    ref = q.float() @ p[:tile_n].float().T
+    qf = torch.zeros(128, 128, device="cuda")
+    qf[:100] = q.float()                                          # rows past the end must read as zero
+    q = qf
+    ref = q @ p[:tile_n].float().T
     err = (out - ref).abs()
     if not (err.max() < 1e-3):
         bad = (err > 1e-3)

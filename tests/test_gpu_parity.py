@@ -170,23 +170,26 @@ def test_all_tilings_agree_bitwise(lis, oracle):
     want = oracle.score_multi_vector_widened(qs, ps)
     base = base16 = None
     try:
-        for eh in (1, 2):
-            for nt, grp in [(256, 1), (256, 2), (256, 3), (128, 1), (128, 2), (128, 3), (128, 4), (128, 5)]:
-                N.check(lib.lis_set_tuning(nt, grp, 0, eh))
-                got = lis.score_multi_vector(qs, ps, round_mode="f32")
-                assert (got - want).abs().max().item() <= TOL_F32, (nt, grp, eh)
-                if base is None:
-                    base = got
-                assert torch.equal(got, base), (nt, grp, eh)
-                got16 = lis.score_multi_vector(qs, ps)
-                if base16 is None:
-                    base16 = got16
-                assert torch.equal(got16, base16), (nt, grp, eh)
-        N.check(lib.lis_set_tuning(0, 0, 3, 0))   # 3 CTAs only: long per-CTA page ranges
+        ss = [(256, 1), (256, 2), (256, 3), (128, 1), (128, 2), (128, 3), (128, 4), (128, 5)]
+        ts = [(128, 1), (128, 2), (128, 3), (128, 4), (192, 1), (192, 2)]
+        for a_op, tilings in ((1, ss), (2, ts)):
+            for eh in (1, 2):
+                for nt, grp in tilings:
+                    N.check(lib.lis_set_tuning(nt, grp, 0, eh, a_op))
+                    got = lis.score_multi_vector(qs, ps, round_mode="f32")
+                    assert (got - want).abs().max().item() <= TOL_F32, (nt, grp, eh, a_op)
+                    if base is None:
+                        base = got
+                    assert torch.equal(got, base), (nt, grp, eh, a_op)
+                    got16 = lis.score_multi_vector(qs, ps)
+                    if base16 is None:
+                        base16 = got16
+                    assert torch.equal(got16, base16), (nt, grp, eh, a_op)
+        N.check(lib.lis_set_tuning(0, 0, 3, 0, 0))   # 3 CTAs only: long per-CTA page ranges
         got = lis.score_multi_vector(qs, ps, round_mode="f32")
         assert torch.equal(got, base)
     finally:
-        lib.lis_set_tuning(0, 0, 0, 0)
+        lib.lis_set_tuning(0, 0, 0, 0, 0)
 
 
 # ---------------------------------------------------------------------------------------------
