@@ -268,14 +268,15 @@ static int current_device_sm_count() {
 }
 
 // Tiling policy (measured on B200, profiles/).  The op's arithmetic intensity is (query rows) FLOP per
-// page byte, so up to 2 query M tiles the pass is HBM-bound and beyond that tensor-bound.
-//  * <= 2 M tiles: SS form, NT = 256 (64 KB TMA tiles keep enough bytes in flight for HBM).
-//  * more: TS form (queries in tensor memory), NT = 128, up to 4 resident M tiles per pass, passes
-//    balanced (5 -> 3+2).  The SS form tops out at ~73 % tensor-pipe activity because its operand
-//    reads saturate shared memory (profiles/README_r1.md).
+// page byte: up to 2 query M tiles a pass is HBM-bound, beyond that tensor-bound.  In both regimes the
+// SS form with NT = 256 measured best: 64 KB TMA tiles keep HBM saturated, and N = 256 is the only
+// shape whose operand fetch (96 B/clk) does not exceed what shared memory delivers to the tensor
+// pipe.  Up to 3 M tiles stay resident (A 96 KB + 2 B stages of 64 KB); more tiles -> several
+// balanced passes (5 -> 3+2).  The TS form (queries in tensor memory, a_operand = 2) is functionally
+// identical and kept selectable; on a power-capped B200 it measured 3-8 % slower (sweep_r1_v4).
 static void choose_tiling(int64_t n_mtiles, int* nt, int* g, bool* atm) {
   if (g_tuning.a_operand) *atm = g_tuning.a_operand == 2;
-  else *atm = n_mtiles > 2;
+  else *atm = false;
   if (g_tuning.tile_n) *nt = g_tuning.tile_n;
   else *nt = *atm ? 128 : 256;
   int gmax = max_group(*nt, *atm);

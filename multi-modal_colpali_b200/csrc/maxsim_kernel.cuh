@@ -305,7 +305,8 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       int64_t p = pa;                                   // current page
       int64_t pend = __ldg(args.p_offsets + p + 1);     // its end row (global)
       uint32_t use = 0;
-      constexpr int GRP = NOWN < 4 ? NOWN : 4;          // chunks held in registers at once
+      constexpr int GRP = (NOWN % 4 == 0) ? 4 : (NOWN % 3 == 0 ? 3 : 2);  // chunks held in registers at once
+      static_assert(NOWN % GRP == 0, "chunk grouping");
       for (int t = 0; t < ntiles; ++t) {
         const int64_t trow = row0 + (int64_t)t * NT;    // global row of column 0
         // end column of a page relative to this tile (saturated; > NT: the page continues)
