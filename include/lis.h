@@ -43,7 +43,8 @@ enum lis_status {
   LIS_E_NOMEM = -4
 };
 
-enum lis_dtype { LIS_BF16 = 0, LIS_F16 = 1 };
+/* LIS_F32X2: fp32 embeddings held as two bf16 planes (hi = bf16(x), lo = bf16(x - hi)); index dtype only */
+enum lis_dtype { LIS_BF16 = 0, LIS_F16 = 1, LIS_F32X2 = 2 };
 
 /* Epilogue rounding.  LIS_ROUND_F32: fp32 max and fp32 sum (accuracy mode, checked at 1e-4
  * against the fp32-widened oracle).  LIS_ROUND_REFERENCE: reproduce what torch does to 16-bit
@@ -97,6 +98,18 @@ int lis_maxsim_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, cons
                       const int32_t* mt_seg, int64_t n_seg, int64_t n_mtiles, const void* tokens,
                       int64_t n_rows, const int64_t* p_offsets, const uint8_t* p_clamp, int64_t np,
                       int dtype, int round_mode, float* out, int64_t ld_out, void* stream);
+
+/* fp32 embeddings (ColFlor's default dtype, 05_experiment02.py:343-347) on the bf16 tensor pipe:
+ * every operand is split into two bf16 planes, x = hi + lo, and a tile product is computed as
+ * hi*hi + hi*lo + lo*hi in fp32 accumulators (error ~1e-6 on unit-norm rows).  lis_split_f32 produces
+ * the planes of a [rows,128] fp32 matrix (device pointers, 16-byte aligned); the scoring call takes
+ * the planes of the packed queries and of the token store and otherwise behaves like
+ * lis_maxsim_scores with LIS_ROUND_F32 (torch computes fp32 inputs in fp32: nothing to emulate). */
+int lis_split_f32(const float* src, int64_t rows, void* hi, void* lo, void* stream);
+int lis_maxsim_scores_f32x2(const void* q_hi, const void* q_lo, int64_t q_rows, const int32_t* seg_lo,
+                            const int32_t* seg_hi, const int32_t* mt_seg, int64_t n_seg, int64_t n_mtiles,
+                            const void* tok_hi, const void* tok_lo, int64_t n_rows, const int64_t* p_offsets,
+                            const uint8_t* p_clamp, int64_t np, float* out, int64_t ld_out, void* stream);
 
 /* out[q, p] = sum of seg_scores[s, p] over the segments s of query q, in segment order.
  * Only needed when some query was cut (n_seg != nq); in that case pass round_mode |
@@ -160,7 +173,8 @@ typedef struct lis_index lis_index;
 
 int lis_index_create(lis_index** out, int device, int dtype, int64_t cap_rows, int64_t cap_pages);
 void lis_index_destroy(lis_index* idx);
-/* Append n pages.  `tokens` [sum(lens),128] may be a host or device pointer (cudaMemcpyDefault);
+/* Append n pages.  `tokens` [sum(lens),128] (16-bit elements, or float for an LIS_F32X2 index) may be
+ * a host or device pointer (cudaMemcpyDefault);
  * lens host int32 [n]; ids host int64 [n] or NULL (then ids continue from the current count);
  * clamp host uint8 [n] or NULL (0).  Synchronous with respect to `stream` on return. */
 int lis_index_add(lis_index* idx, const void* tokens, const int32_t* lens, const int64_t* ids,
@@ -168,7 +182,8 @@ int lis_index_add(lis_index* idx, const void* tokens, const int32_t* lens, const
 int64_t lis_index_num_pages(const lis_index* idx);
 int64_t lis_index_num_rows(const lis_index* idx);
 /* Raw views (device pointers) for zero-copy use by the stateless entry points. */
-const void* lis_index_tokens(const lis_index* idx);
+const void* lis_index_tokens(const lis_index* idx);    /* 16-bit rows; the hi plane of an LIS_F32X2 index */
+const void* lis_index_tokens_lo(const lis_index* idx); /* lo plane of an LIS_F32X2 index, else NULL */
 const int64_t* lis_index_offsets(const lis_index* idx);
 const int64_t* lis_index_ids(const lis_index* idx);
 const uint8_t* lis_index_clamp(const lis_index* idx);
@@ -177,15 +192,17 @@ const uint8_t* lis_index_clamp(const lis_index* idx);
  * host.  lens host int32 [n] or NULL (then every page has fixed_len rows).  Ids run from id_base. */
 int lis_index_fill_synthetic(lis_index* idx, int64_t n, const int32_t* lens, int32_t fixed_len,
                              uint64_t seed, int64_t id_base, void* stream);
-/* Copy token rows [row0, row0+n_rows) of the store to `dst` (host or device), synchronously. */
+/* Copy token rows [row0, row0+n_rows) of the store to `dst` (host or device), synchronously
+ * (16-bit rows; float rows hi+lo for an LIS_F32X2 index). */
 int lis_index_read_rows(const lis_index* idx, int64_t row0, int64_t n_rows, void* dst, void* stream);
 /* Stateless version of the generator: fill dst[n_rows,128] (device) with the rows the hash assigns
  * to global row indices row0 .. row0+n_rows-1. */
 int lis_fill_synthetic_rows(void* dst, int64_t row0, int64_t n_rows, uint64_t seed, int dtype, void* stream);
-/* Search: packed queries (as for lis_maxsim_scores) -> top-k (score, id) per query.
+/* Search: packed queries (as for lis_maxsim_scores; for an LIS_F32X2 index `q` is the hi plane and
+ * `q_lo` the lo plane, else q_lo = NULL) -> top-k (score, id) per query.
  * Requires n_seg == nq (no split queries) unless seg_first != NULL (device int32 [nq+1]).
  * Scratch is owned by the index and grown on demand (outside the timed path after warm-up). */
-int lis_index_search(lis_index* idx, const void* q, int64_t q_rows, const int32_t* seg_lo,
+int lis_index_search(lis_index* idx, const void* q, const void* q_lo, int64_t q_rows, const int32_t* seg_lo,
                      const int32_t* seg_hi, const int32_t* mt_seg, int64_t n_seg, int64_t n_mtiles,
                      const int32_t* seg_first, int64_t nq, int round_mode, int k, float* out_scores,
                      int64_t* out_ids, void* stream);

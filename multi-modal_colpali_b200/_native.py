@@ -20,6 +20,7 @@ LIS_E_NOMEM = -4
 
 LIS_BF16 = 0
 LIS_F16 = 1
+LIS_F32X2 = 2
 ROUND_F32 = 0
 ROUND_REFERENCE = 1
 ROUND_DEFER_SUM = 2
@@ -39,6 +40,9 @@ SIGNATURES = {
     "lis_plan_queries": (_i64, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp]),
     "lis_maxsim_scores": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32,
                                  _vp, _i64, _vp]),
+    "lis_split_f32": (_i32, [_vp, _i64, _vp, _vp, _vp]),
+    "lis_maxsim_scores_f32x2": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i64,
+                                       _vp, _i64, _vp]),
     "lis_reduce_segments": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _i64, _vp]),
     "lis_set_tuning": (_i32, [_i32, _i32, _i32, _i32, _i32]),
     "lis_launch_count": (_i64, []),
@@ -53,13 +57,14 @@ SIGNATURES = {
     "lis_index_num_pages": (_i64, [_vp]),
     "lis_index_num_rows": (_i64, [_vp]),
     "lis_index_tokens": (_vp, [_vp]),
+    "lis_index_tokens_lo": (_vp, [_vp]),
     "lis_index_offsets": (_vp, [_vp]),
     "lis_index_ids": (_vp, [_vp]),
     "lis_index_clamp": (_vp, [_vp]),
     "lis_index_fill_synthetic": (_i32, [_vp, _i64, _vp, _i32, C.c_uint64, _i64, _vp]),
     "lis_index_read_rows": (_i32, [_vp, _i64, _i64, _vp, _vp]),
     "lis_fill_synthetic_rows": (_i32, [_vp, _i64, _i64, C.c_uint64, _i32, _vp]),
-    "lis_index_search": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "lis_index_search": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
 }
 
 _lib = None

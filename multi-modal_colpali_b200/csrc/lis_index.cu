@@ -20,7 +20,7 @@ struct lis_index {
   int dtype = LIS_BF16;
   int64_t cap_rows = 0, cap_pages = 0;
   int64_t n_rows = 0, n_pages = 0;
-  void* tokens = nullptr;
+  void* tokens = nullptr;      // F32X2: hi plane rows [0, cap_rows), lo plane rows [cap_rows, 2*cap_rows)
   int64_t* offsets = nullptr;
   int64_t* ids = nullptr;
   uint8_t* clamp = nullptr;
@@ -80,6 +80,18 @@ fill_rows_kernel(void* __restrict__ dst, int64_t row0, int64_t n_rows, uint64_t 
   }
 }
 
+__global__ void merge_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                    int64_t n, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+}
+
+static inline int planes_of(const lis_index* ix) { return ix->dtype == LIS_F32X2 ? 2 : 1; }
+static inline int elem_dtype(const lis_index* ix) { return ix->dtype == LIS_F32X2 ? LIS_BF16 : ix->dtype; }
+static inline uint8_t* lo_plane(const lis_index* ix) {
+  return static_cast<uint8_t*>(ix->tokens) + (size_t)ix->cap_rows * 256;
+}
+
 static int ensure(void** p, int64_t* have, int64_t need) {
   if (*have >= need) return LIS_OK;
   if (*p) cudaFree(*p);
@@ -120,7 +132,7 @@ int lis_fill_synthetic_rows(void* dst, int64_t row0, int64_t n_rows, uint64_t se
 int lis_index_create(lis_index** out, int device, int dtype, int64_t cap_rows, int64_t cap_pages) {
   LIS_REQUIRE(out, "null out");
   *out = nullptr;
-  LIS_REQUIRE(dtype == LIS_BF16 || dtype == LIS_F16, "dtype must be bf16 or f16");
+  LIS_REQUIRE(dtype == LIS_BF16 || dtype == LIS_F16 || dtype == LIS_F32X2, "dtype must be bf16, f16 or f32x2");
   LIS_REQUIRE(cap_rows > 0 && cap_pages > 0, "capacities must be positive");
   LIS_REQUIRE(cap_rows < (int64_t(1) << 31), "cap_rows must be < 2^31 per index (shard the corpus)");
   int rc = lis_device_supported(device);
@@ -131,7 +143,7 @@ int lis_index_create(lis_index** out, int device, int dtype, int64_t cap_rows, i
   ix->dtype = dtype;
   ix->cap_rows = cap_rows;
   ix->cap_pages = cap_pages;
-  cudaError_t e = cudaMalloc(&ix->tokens, (size_t)cap_rows * 256);
+  cudaError_t e = cudaMalloc(&ix->tokens, (size_t)cap_rows * 256 * (dtype == LIS_F32X2 ? 2 : 1));
   if (e == cudaSuccess) e = cudaMalloc((void**)&ix->offsets, (size_t)(cap_pages + 1) * 8);
   if (e == cudaSuccess) e = cudaMalloc((void**)&ix->ids, (size_t)cap_pages * 8);
   if (e == cudaSuccess) e = cudaMalloc((void**)&ix->clamp, (size_t)cap_pages);
@@ -161,6 +173,7 @@ void lis_index_destroy(lis_index* ix) {
 int64_t lis_index_num_pages(const lis_index* ix) { return ix ? ix->n_pages : 0; }
 int64_t lis_index_num_rows(const lis_index* ix) { return ix ? ix->n_rows : 0; }
 const void* lis_index_tokens(const lis_index* ix) { return ix ? ix->tokens : nullptr; }
+const void* lis_index_tokens_lo(const lis_index* ix) { return ix && ix->dtype == LIS_F32X2 ? lo_plane(ix) : nullptr; }
 const int64_t* lis_index_offsets(const lis_index* ix) { return ix ? ix->offsets : nullptr; }
 const int64_t* lis_index_ids(const lis_index* ix) { return ix ? ix->ids : nullptr; }
 const uint8_t* lis_index_clamp(const lis_index* ix) { return ix ? ix->clamp : nullptr; }
@@ -205,9 +218,20 @@ int lis_index_add(lis_index* ix, const void* tokens, const int32_t* lens, const 
   if (rc) return rc;
   if (new_rows > 0) {
     LIS_REQUIRE(tokens, "lis_index_add: null tokens");
-    LIS_CUDA_CHECK(cudaMemcpyAsync(static_cast<uint8_t*>(ix->tokens) + ix->n_rows * 256, tokens,
-                                   (size_t)new_rows * 256, cudaMemcpyDefault, st));
-    LIS_CUDA_CHECK(cudaStreamSynchronize(st));
+    uint8_t* hi = static_cast<uint8_t*>(ix->tokens) + ix->n_rows * 256;
+    if (ix->dtype == LIS_F32X2) {
+      float* stage = nullptr;  // fp32 rows land in a staging buffer, then get split into the planes
+      LIS_CUDA_CHECK(cudaMalloc((void**)&stage, (size_t)new_rows * 512));
+      cudaError_t e = cudaMemcpyAsync(stage, tokens, (size_t)new_rows * 512, cudaMemcpyDefault, st);
+      int rc2 = e == cudaSuccess ? lis_split_f32(stage, new_rows, hi, lo_plane(ix) + ix->n_rows * 256, stream) : LIS_E_CUDA;
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      cudaFree(stage);
+      if (e != cudaSuccess) { set_error("index add (fp32) failed: %s", cudaGetErrorString(e)); return LIS_E_CUDA; }
+      if (rc2) return rc2;
+    } else {
+      LIS_CUDA_CHECK(cudaMemcpyAsync(hi, tokens, (size_t)new_rows * 256, cudaMemcpyDefault, st));
+      LIS_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
   }
   ix->n_rows += new_rows;
   ix->n_pages += n;
@@ -226,8 +250,10 @@ int lis_index_fill_synthetic(lis_index* ix, int64_t n, const int32_t* lens, int3
   // global row index = id_base-independent position in this index; callers that shard a corpus
   // pass distinct seeds per shard
   rc = lis_fill_synthetic_rows(static_cast<uint8_t*>(ix->tokens) + ix->n_rows * 256, ix->n_rows, new_rows, seed,
-                               ix->dtype, stream);
+                               elem_dtype(ix), stream);
   if (rc) return rc;
+  if (ix->dtype == LIS_F32X2)  // synthetic rows are exactly representable in bf16: the lo plane is zero
+    LIS_CUDA_CHECK(cudaMemsetAsync(lo_plane(ix) + ix->n_rows * 256, 0, (size_t)new_rows * 256, st));
   LIS_CUDA_CHECK(cudaStreamSynchronize(st));
   ix->n_rows += new_rows;
   ix->n_pages += n;
@@ -239,13 +265,27 @@ int lis_index_read_rows(const lis_index* ix, int64_t row0, int64_t n_rows, void*
   LIS_REQUIRE(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= ix->n_rows, "row range out of bounds");
   if (n_rows == 0) return LIS_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (ix->dtype == LIS_F32X2) {
+    float* stage = nullptr;
+    LIS_CUDA_CHECK(cudaMalloc((void**)&stage, (size_t)n_rows * 512));
+    const int64_t n = n_rows * 128;
+    merge_planes_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 65535), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(static_cast<const uint8_t*>(ix->tokens) + row0 * 256),
+        reinterpret_cast<const __nv_bfloat16*>(lo_plane(ix) + row0 * 256), n, stage);
+    count_launch();
+    cudaError_t e = cudaMemcpyAsync(dst, stage, (size_t)n_rows * 512, cudaMemcpyDefault, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(stage);
+    LIS_CUDA_CHECK(e);
+    return LIS_OK;
+  }
   LIS_CUDA_CHECK(cudaMemcpyAsync(dst, static_cast<const uint8_t*>(ix->tokens) + row0 * 256, (size_t)n_rows * 256,
                                  cudaMemcpyDefault, st));
   LIS_CUDA_CHECK(cudaStreamSynchronize(st));
   return LIS_OK;
 }
 
-int lis_index_search(lis_index* ix, const void* q, int64_t q_rows, const int32_t* seg_lo, const int32_t* seg_hi,
+int lis_index_search(lis_index* ix, const void* q, const void* q_lo, int64_t q_rows, const int32_t* seg_lo, const int32_t* seg_hi,
                      const int32_t* mt_seg, int64_t n_seg, int64_t n_mtiles, const int32_t* seg_first, int64_t nq,
                      int round_mode, int k, float* out_scores, int64_t* out_ids, void* stream) {
   LIS_REQUIRE(ix, "null index");
@@ -260,14 +300,21 @@ int lis_index_search(lis_index* ix, const void* q, int64_t q_rows, const int32_t
   rc = ensure(&ix->topk_ws, &ix->topk_ws_bytes, ws_need);
   if (rc) return rc;
   const int k1_round = (n_seg != nq) ? (round_mode | LIS_ROUND_DEFER_SUM) : round_mode;
-  rc = lis_maxsim_scores(q, q_rows, seg_lo, seg_hi, mt_seg, n_seg, n_mtiles, ix->tokens, ix->n_rows, ix->offsets,
-                         ix->clamp, np, ix->dtype, k1_round, ix->seg_scores, np, stream);
+  if (ix->dtype == LIS_F32X2) {
+    LIS_REQUIRE(q_lo, "an f32x2 index needs the low plane of the queries");
+    round_mode = LIS_ROUND_F32;
+    rc = lis_maxsim_scores_f32x2(q, q_lo, q_rows, seg_lo, seg_hi, mt_seg, n_seg, n_mtiles, ix->tokens, lo_plane(ix),
+                                 ix->n_rows, ix->offsets, ix->clamp, np, ix->seg_scores, np, stream);
+  } else {
+    rc = lis_maxsim_scores(q, q_rows, seg_lo, seg_hi, mt_seg, n_seg, n_mtiles, ix->tokens, ix->n_rows, ix->offsets,
+                           ix->clamp, np, ix->dtype, k1_round, ix->seg_scores, np, stream);
+  }
   if (rc) return rc;
   const float* scores = ix->seg_scores;
   if (n_seg != nq) {
     rc = ensure((void**)&ix->q_scores, &ix->q_scores_bytes, nq * np * 4);
     if (rc) return rc;
-    rc = lis_reduce_segments(ix->seg_scores, np, seg_first, nq, np, round_mode, ix->dtype, ix->q_scores, np, stream);
+    rc = lis_reduce_segments(ix->seg_scores, np, seg_first, nq, np, round_mode, elem_dtype(ix), ix->q_scores, np, stream);
     if (rc) return rc;
     scores = ix->q_scores;
   }

@@ -76,11 +76,14 @@ int sm_count(int device) {
 constexpr int kSmemBudget = 232448;  // 227 KB opt-in maximum per CTA on sm_100
 constexpr int kSmemTail = 3072;      // barriers (240 B) + row-max exchange (<= 2048 B)
 
-template <int NT, int G, int EH, bool ATM, bool DBG>
-static int launch_maxsim(const CUtensorMap& tq, const CUtensorMap& tp, const MaxSimArgs& a, int grid,
-                         cudaStream_t st) {
-  const int stage = NT * kDim * 2;
-  const int a_bytes = ATM ? 0 : G * kATileBytes;
+struct Maps {
+  CUtensorMap q, p, q2, p2;  // q2/p2: low planes of split-fp32 operands (copies of q/p otherwise)
+};
+
+template <int NT, int G, int EH, bool ATM, bool DBG, int P = 1>
+static int launch_maxsim(const Maps& m, const MaxSimArgs& a, int grid, cudaStream_t st) {
+  const int stage = P * NT * kDim * 2;
+  const int a_bytes = ATM ? 0 : P * G * kATileBytes;
   int ns = (kSmemBudget - kSmemTail - a_bytes) / stage;
   ns = std::min(ns, 8);
   if (ns < 1) {
@@ -92,7 +95,7 @@ static int launch_maxsim(const CUtensorMap& tq, const CUtensorMap& tp, const Max
     set_error("internal: n_mt=%d must equal the instantiated group %d", a.n_mt, G);
     return LIS_E_INVALID;
   }
-  auto kern = maxsim_kernel<NT, G, EH, ATM, DBG>;
+  auto kern = maxsim_kernel<NT, G, EH, ATM, DBG, P>;
   static bool configured[64] = {false};  // per template instantiation and device
   int dev = 0;
   LIS_CUDA_CHECK(cudaGetDevice(&dev));
@@ -100,7 +103,7 @@ static int launch_maxsim(const CUtensorMap& tq, const CUtensorMap& tp, const Max
     LIS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  kern<<<grid, 64 + 128 * EH, smem, st>>>(tq, tp, a, ns);
+  kern<<<grid, 64 + 128 * EH, smem, st>>>(m.q, m.p, m.q2, m.p2, a, ns);
   count_launch();
   LIS_CUDA_CHECK(cudaGetLastError());
   return LIS_OK;
@@ -108,19 +111,24 @@ static int launch_maxsim(const CUtensorMap& tq, const CUtensorMap& tp, const Max
 
 // Instantiations.  SS form (A in shared memory): NT 256 x G 1..3, NT 128 x G 1..5.
 // TS form (A in tensor memory): 64*G + NACC*NT <= 512 columns -> NT 128 x G 1..4, NT 192 x G 1..2.
-static int dispatch_maxsim(int nt, int g, bool atm, const CUtensorMap& tq, const CUtensorMap& tp,
-                           const MaxSimArgs& a, int grid, cudaStream_t st, bool dbg = false) {
+static int dispatch_maxsim(int nt, int g, bool atm, const Maps& m, const MaxSimArgs& a, int grid,
+                           cudaStream_t st, bool dbg = false, int planes = 1) {
+  if (planes == 2) {  // split fp32: one resident M tile (2 planes) + 2 stages of 2-plane 128-row tiles
+    if (g == 1) return launch_maxsim<128, 1, 2, false, false, 2>(m, a, grid, st);
+    set_error("split-fp32 scoring runs one M tile per pass");
+    return LIS_E_INVALID;
+  }
   if (dbg) {
-    if (nt == 256 && g == 1 && !atm) return launch_maxsim<256, 1, 2, false, true>(tq, tp, a, grid, st);
-    if (nt == 128 && g == 1 && !atm) return launch_maxsim<128, 1, 1, false, true>(tq, tp, a, grid, st);
-    if (nt == 128 && g == 1 && atm) return launch_maxsim<128, 1, 2, true, true>(tq, tp, a, grid, st);
-    if (nt == 192 && g == 1 && atm) return launch_maxsim<192, 1, 2, true, true>(tq, tp, a, grid, st);
+    if (nt == 256 && g == 1 && !atm) return launch_maxsim<256, 1, 2, false, true>(m, a, grid, st);
+    if (nt == 128 && g == 1 && !atm) return launch_maxsim<128, 1, 1, false, true>(m, a, grid, st);
+    if (nt == 128 && g == 1 && atm) return launch_maxsim<128, 1, 2, true, true>(m, a, grid, st);
+    if (nt == 192 && g == 1 && atm) return launch_maxsim<192, 1, 2, true, true>(m, a, grid, st);
   }
   const int eh = g_tuning.epi_halves ? g_tuning.epi_halves : 2;
 #define LIS_CASE(NT_, G_, ATM_)                                                                \
   if (nt == NT_ && g == G_ && atm == ATM_)                                                     \
-    return eh == 2 ? launch_maxsim<NT_, G_, 2, ATM_, false>(tq, tp, a, grid, st)               \
-                   : launch_maxsim<NT_, G_, 1, ATM_, false>(tq, tp, a, grid, st);
+    return eh == 2 ? launch_maxsim<NT_, G_, 2, ATM_, false>(m, a, grid, st)                    \
+                   : launch_maxsim<NT_, G_, 1, ATM_, false>(m, a, grid, st);
   LIS_CASE(256, 1, false) LIS_CASE(256, 2, false) LIS_CASE(256, 3, false)
   LIS_CASE(128, 1, false) LIS_CASE(128, 2, false) LIS_CASE(128, 3, false) LIS_CASE(128, 4, false)
   LIS_CASE(128, 5, false)
@@ -292,32 +300,46 @@ static void choose_tiling(int64_t n_mtiles, int* nt, int* g, bool* atm) {
   *g = (int)((n_mtiles + passes - 1) / passes);
 }
 
-int lis_maxsim_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, const int32_t* seg_hi,
-                      const int32_t* mt_seg, int64_t n_seg, int64_t n_mtiles, const void* tokens,
-                      int64_t n_rows, const int64_t* p_offsets, const uint8_t* p_clamp, int64_t np,
-                      int dtype, int round_mode, float* out, int64_t ld_out, void* stream) {
-  LIS_REQUIRE(q && seg_lo && seg_hi && mt_seg && p_offsets && out, "lis_maxsim_scores: null pointer");
-  LIS_REQUIRE(dtype == LIS_BF16 || dtype == LIS_F16, "lis_maxsim_scores: dtype must be bf16 or f16");
+static int maxsim_impl(const void* q, const void* q_lo, int64_t q_rows, const int32_t* seg_lo, const int32_t* seg_hi,
+                       const int32_t* mt_seg, int64_t n_seg, int64_t n_mtiles, const void* tokens,
+                       const void* tokens_lo, int64_t n_rows, const int64_t* p_offsets, const uint8_t* p_clamp,
+                       int64_t np, int dtype, int round_mode, float* out, int64_t ld_out, void* stream) {
+  const int planes = q_lo ? 2 : 1;
+  LIS_REQUIRE(q && seg_lo && seg_hi && mt_seg && p_offsets && out, "maxsim: null pointer");
+  LIS_REQUIRE(dtype == LIS_BF16 || dtype == LIS_F16, "maxsim: dtype must be bf16 or f16");
   LIS_REQUIRE(round_mode >= 0 && round_mode <= 3, "bad round_mode");
-  LIS_REQUIRE(n_seg > 0 && n_mtiles > 0 && np > 0, "lis_maxsim_scores: empty problem (n_seg=%lld np=%lld)",
+  LIS_REQUIRE(n_seg > 0 && n_mtiles > 0 && np > 0, "maxsim: empty problem (n_seg=%lld np=%lld)",
               (long long)n_seg, (long long)np);
-  LIS_REQUIRE(q_rows > 0 && q_rows > (n_mtiles - 1) * kMTile, "q_rows=%lld inconsistent with n_mtiles=%lld",
-              (long long)q_rows, (long long)n_mtiles);
+  LIS_REQUIRE(q_rows > 0 && q_rows > (n_mtiles - 1) * kMTile && q_rows <= n_mtiles * kMTile,
+              "q_rows=%lld inconsistent with n_mtiles=%lld", (long long)q_rows, (long long)n_mtiles);
   LIS_REQUIRE(ld_out >= np, "ld_out < np");
   LIS_REQUIRE(n_rows >= 0, "n_rows < 0");
+  LIS_REQUIRE(n_rows == 0 || tokens, "maxsim: null token store");
+  LIS_REQUIRE(planes == 1 || n_rows == 0 || tokens_lo, "maxsim: null low plane");
   cudaStream_t st = (cudaStream_t)stream;
   int sms = current_device_sm_count();
   LIS_REQUIRE(sms > 0, "no CUDA device");
 
-  CUtensorMap tq, tp;
-  int rc = encode_rows_tmap(&tq, q, q_rows, kMTile, dtype);
-  if (rc) return rc;
   int nt, g;
   bool atm;
-  choose_tiling(n_mtiles, &nt, &g, &atm);
-  // an empty token store still needs a valid map: point it at the query rows (never loaded)
-  rc = n_rows > 0 ? encode_rows_tmap(&tp, tokens, n_rows, nt, dtype) : encode_rows_tmap(&tp, q, q_rows, nt, dtype);
+  if (planes == 2) { nt = 128; g = 1; atm = false; }
+  else choose_tiling(n_mtiles, &nt, &g, &atm);
+  Maps m;
+  int rc = encode_rows_tmap(&m.q, q, q_rows, kMTile, dtype);
   if (rc) return rc;
+  // an empty token store still needs a valid map: point it at the query rows (never loaded)
+  rc = n_rows > 0 ? encode_rows_tmap(&m.p, tokens, n_rows, nt, dtype) : encode_rows_tmap(&m.p, q, q_rows, nt, dtype);
+  if (rc) return rc;
+  m.q2 = m.q;
+  m.p2 = m.p;
+  if (planes == 2) {
+    rc = encode_rows_tmap(&m.q2, q_lo, q_rows, kMTile, dtype);
+    if (rc) return rc;
+    if (n_rows > 0) {
+      rc = encode_rows_tmap(&m.p2, tokens_lo, n_rows, nt, dtype);
+      if (rc) return rc;
+    }
+  }
 
   int grid = sms;
   if (g_tuning.max_ctas > 0) grid = std::min(grid, g_tuning.max_ctas);
@@ -341,9 +363,59 @@ int lis_maxsim_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, cons
     a.round_mode = round_mode;
     a.is_bf16 = dtype == LIS_BF16;
     // the instantiation whose group equals this pass's tile count (the last pass may be short)
-    rc = dispatch_maxsim(nt, a.n_mt, atm, tq, tp, a, grid, st);
+    rc = dispatch_maxsim(nt, a.n_mt, atm, m, a, grid, st, false, planes);
     if (rc) return rc;
   }
+  return LIS_OK;
+}
+
+int lis_maxsim_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, const int32_t* seg_hi,
+                      const int32_t* mt_seg, int64_t n_seg, int64_t n_mtiles, const void* tokens,
+                      int64_t n_rows, const int64_t* p_offsets, const uint8_t* p_clamp, int64_t np,
+                      int dtype, int round_mode, float* out, int64_t ld_out, void* stream) {
+  return maxsim_impl(q, nullptr, q_rows, seg_lo, seg_hi, mt_seg, n_seg, n_mtiles, tokens, nullptr, n_rows, p_offsets,
+                     p_clamp, np, dtype, round_mode, out, ld_out, stream);
+}
+
+int lis_maxsim_scores_f32x2(const void* q_hi, const void* q_lo, int64_t q_rows, const int32_t* seg_lo,
+                            const int32_t* seg_hi, const int32_t* mt_seg, int64_t n_seg, int64_t n_mtiles,
+                            const void* tok_hi, const void* tok_lo, int64_t n_rows, const int64_t* p_offsets,
+                            const uint8_t* p_clamp, int64_t np, float* out, int64_t ld_out, void* stream) {
+  LIS_REQUIRE(q_lo, "lis_maxsim_scores_f32x2: null low plane");
+  return maxsim_impl(q_hi, q_lo, q_rows, seg_lo, seg_hi, mt_seg, n_seg, n_mtiles, tok_hi, tok_lo, n_rows, p_offsets,
+                     p_clamp, np, LIS_BF16, LIS_ROUND_F32, out, ld_out, stream);
+}
+
+namespace lis {
+// x = hi + lo + O(2^-18 |x|):  hi = bf16(x),  lo = bf16(x - hi)
+__global__ void split_f32_kernel(const float4* __restrict__ src, int64_t n4, uint2* __restrict__ hi,
+                                 uint2* __restrict__ lo) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 x = __ldg(src + i);
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y);
+    const __nv_bfloat16 h2 = __float2bfloat16_rn(x.z), h3 = __float2bfloat16_rn(x.w);
+    const __nv_bfloat162 ha = __halves2bfloat162(h0, h1), hb = __halves2bfloat162(h2, h3);
+    const __nv_bfloat162 la = __floats2bfloat162_rn(x.x - __bfloat162float(h0), x.y - __bfloat162float(h1));
+    const __nv_bfloat162 lb = __floats2bfloat162_rn(x.z - __bfloat162float(h2), x.w - __bfloat162float(h3));
+    hi[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
+    lo[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
+  }
+}
+}  // namespace lis
+
+int lis_split_f32(const float* src, int64_t rows, void* hi, void* lo, void* stream) {
+  LIS_REQUIRE(rows >= 0, "negative row count");
+  if (rows == 0) return LIS_OK;
+  LIS_REQUIRE(src && hi && lo, "lis_split_f32: null pointer");
+  LIS_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0,
+              "lis_split_f32: pointers must be 16-byte aligned");
+  const int64_t n4 = rows * (kDim / 4);
+  const int sms = current_device_sm_count();
+  const unsigned grid = (unsigned)std::min<int64_t>((n4 + 255) / 256, (int64_t)std::max(sms, 1) * 32);
+  split_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src), n4,
+                                                          static_cast<uint2*>(hi), static_cast<uint2*>(lo));
+  count_launch();
+  LIS_CUDA_CHECK(cudaGetLastError());
   return LIS_OK;
 }
 
@@ -363,11 +435,13 @@ int lis_debug_sim_tile(const void* q, int64_t q_rows, const void* tokens, int64_
               "tile_n must be 128/256 (shared-memory A) or 128/192 (tensor-memory A)");
   LIS_REQUIRE(q_rows > 0 && n_rows > 0, "empty input");
   cudaStream_t st = (cudaStream_t)stream;
-  CUtensorMap tq, tp;
-  int rc = encode_rows_tmap(&tq, q, q_rows, kMTile, dtype);
+  Maps m;
+  int rc = encode_rows_tmap(&m.q, q, q_rows, kMTile, dtype);
   if (rc) return rc;
-  rc = encode_rows_tmap(&tp, tokens, n_rows, tile_n, dtype);
+  rc = encode_rows_tmap(&m.p, tokens, n_rows, tile_n, dtype);
   if (rc) return rc;
+  m.q2 = m.q;
+  m.p2 = m.p;
   // scratch tables + a dummy score
   char* scratch = nullptr;
   LIS_CUDA_CHECK(cudaMalloc(&scratch, 256));
@@ -384,7 +458,7 @@ int lis_debug_sim_tile(const void* q, int64_t q_rows, const void* tokens, int64_
   a.is_bf16 = dtype == LIS_BF16;
   a.q = q;
   a.q_rows = q_rows;
-  rc = dispatch_maxsim(tile_n, 1, a_in_tmem != 0, tq, tp, a, 1, st, true);
+  rc = dispatch_maxsim(tile_n, 1, a_in_tmem != 0, m, a, 1, st, true);
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(scratch);
   if (rc) return rc;

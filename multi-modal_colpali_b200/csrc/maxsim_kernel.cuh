@@ -94,21 +94,30 @@ __device__ __forceinline__ int64_t lower_bound_off(const int64_t* off, int64_t n
 // serves only the page tiles: the SS form at M=128 x N=256 reads 96 B/clk of operands from smem,
 // which is the measured operand-fetch limit (profiles/micro_mma_rate_r1.txt), so every TMA write
 // competes with the tensor pipe; with A in TMEM the MMA reads 64 B/clk at any N.
-template <int NT, int G, int EH, bool ATM, bool DBG>
+//
+// P ("planes"): fp32 embeddings are served as two bf16 planes per operand, x = hi + lo with
+// hi = bf16(x), lo = bf16(x - hi) (|x - hi - lo| <= 2^-18 |x|).  The tile product is then
+// hi*hi + hi*lo + lo*hi, three MMAs into the same fp32 accumulator (the dropped lo*lo term is of
+// the order of the residual), which keeps ~fp32 accuracy on the bf16 tensor pipe.
+template <int NT, int G, int EH, bool ATM, bool DBG, int P = 1>
 __global__ void __launch_bounds__(64 + 128 * EH, 1)
 maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_p,
+              const __grid_constant__ CUtensorMap tmap_q2, const __grid_constant__ CUtensorMap tmap_p2,
               const MaxSimArgs args, const int NS) {
+  static_assert(P == 1 || (P == 2 && !ATM), "planes");
   static_assert(NT == 128 || NT == 192 || NT == 256, "tile_n");
   static_assert(EH == 1 || EH == 2, "epilogue halves");
   constexpr int kACols = ATM ? 64 * G : 0;              // TMEM columns holding the query tiles
   constexpr int NACC = (kTmemCols - kACols) / NT;       // accumulator buffers
   static_assert(NACC >= 2 && NACC <= 4, "need at least two accumulator buffers");
-  constexpr int kBStageBytes = NT * kDim * 2;
+  constexpr int kBPlaneBytes = NT * kDim * 2;
+  constexpr int kBStageBytes = P * kBPlaneBytes;
   constexpr int kBHalfBytes = NT * 128;
+  constexpr int kATile = P * kATileBytes;               // all planes of one M tile
 
   extern __shared__ __align__(1024) uint8_t smem[];  // 128-byte swizzle atoms need 1024-byte alignment
-  uint8_t* smem_a = smem;                               // [G][2][128 rows x 128 B] (SS form only)
-  uint8_t* smem_b = smem + (ATM ? 0 : G * kATileBytes); // [NS][2][NT rows x 128 B]
+  uint8_t* smem_a = smem;                               // [G][P][2][128 rows x 128 B] (SS form only)
+  uint8_t* smem_b = smem + (ATM ? 0 : G * kATile);      // [NS][P][2][NT rows x 128 B]
   uint8_t* tail = smem_b + (size_t)NS * kBStageBytes;
   uint64_t* q_full = reinterpret_cast<uint64_t*>(tail);      // 1
   uint64_t* b_full = q_full + 1;                             // [NS]
@@ -125,6 +134,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_p);
+    if (P == 2) { tma_prefetch_desc(&tmap_q2); tma_prefetch_desc(&tmap_p2); }
     mbar_init(q_full, ATM ? 4 * EH : 1);
     for (int s = 0; s < NS; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
     for (int a = 0; a < NACC; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, 4 * EH); }
@@ -167,11 +177,12 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0 && pa < pb) {
       if (!ATM && ntiles > 0) {
-        mbar_arrive_expect_tx(q_full, (uint32_t)n_mt * kATileBytes);
+        mbar_arrive_expect_tx(q_full, (uint32_t)n_mt * kATile);
         for (int g = 0; g < n_mt; ++g)
-          for (int h = 0; h < 2; ++h)
-            tma_load_2d(smem_a + g * kATileBytes + h * (kMTile * 128), &tmap_q, q_full, h * kKHalf,
-                        (args.mt0 + g) * kMTile, kPolicyEvictLast);
+          for (int pl = 0; pl < P; ++pl)
+            for (int h = 0; h < 2; ++h)
+              tma_load_2d(smem_a + g * kATile + pl * kATileBytes + h * (kMTile * 128), pl ? &tmap_q2 : &tmap_q,
+                          q_full, h * kKHalf, (args.mt0 + g) * kMTile, kPolicyEvictLast);
       }
       for (int t = 0; t < ntiles; ++t) {
         const int s = t % NS;
@@ -180,8 +191,11 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         mbar_arrive_expect_tx(b_full + s, kBStageBytes);
         uint8_t* dst = smem_b + (size_t)s * kBStageBytes;
         const int32_t r = (int32_t)(row0 + (int64_t)t * NT);
-        tma_load_2d(dst, &tmap_p, b_full + s, 0, r, kPolicyEvictFirst);
-        tma_load_2d(dst + kBHalfBytes, &tmap_p, b_full + s, kKHalf, r, kPolicyEvictFirst);
+        for (int pl = 0; pl < P; ++pl) {
+          const CUtensorMap* tm = pl ? &tmap_p2 : &tmap_p;
+          tma_load_2d(dst + pl * kBPlaneBytes, tm, b_full + s, 0, r, kPolicyEvictFirst);
+          tma_load_2d(dst + pl * kBPlaneBytes + kBHalfBytes, tm, b_full + s, kKHalf, r, kPolicyEvictFirst);
+        }
       }
     }
   } else if (warp == 1) {
@@ -201,17 +215,24 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           mbar_wait(acc_empty + a, ((use / NACC) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + kACols + a * NT;
+          // plane pairs (A plane, B plane): hi*hi only, or hi*hi + hi*lo + lo*hi for split fp32
 #pragma unroll
-          for (int k = 0; k < kDim / 16; ++k) {
-            const uint32_t koff = (uint32_t)(k >> 2) * (kMTile * 128) + (uint32_t)(k & 3) * 32;
-            const uint32_t koff_b = (uint32_t)(k >> 2) * kBHalfBytes + (uint32_t)(k & 3) * 32;
-            const uint64_t bdesc = make_kmajor_sw128_desc(b_base + s * kBStageBytes + koff_b);
-            if (ATM) {
-              // 16 K-elements of a 16-bit operand = 8 TMEM columns per k-step
-              umma_f16_ts(d_tmem, tmem_base + g * 64 + k * 8, bdesc, idesc, k > 0 ? 1u : 0u);
-            } else {
-              const uint64_t adesc = make_kmajor_sw128_desc(a_base + g * kATileBytes + koff);
-              umma_f16(d_tmem, adesc, bdesc, idesc, k > 0 ? 1u : 0u);
+          for (int pp = 0; pp < (P == 2 ? 3 : 1); ++pp) {
+            const uint32_t pa_off = (pp == 2 ? 1u : 0u) * kATileBytes;
+            const uint32_t pb_off = (pp == 1 ? 1u : 0u) * kBPlaneBytes;
+#pragma unroll
+            for (int k = 0; k < kDim / 16; ++k) {
+              const uint32_t koff = (uint32_t)(k >> 2) * (kMTile * 128) + (uint32_t)(k & 3) * 32;
+              const uint32_t koff_b = (uint32_t)(k >> 2) * kBHalfBytes + (uint32_t)(k & 3) * 32;
+              const uint64_t bdesc = make_kmajor_sw128_desc(b_base + s * kBStageBytes + pb_off + koff_b);
+              const uint32_t acc = (pp | k) ? 1u : 0u;
+              if (ATM) {
+                // 16 K-elements of a 16-bit operand = 8 TMEM columns per k-step
+                umma_f16_ts(d_tmem, tmem_base + g * 64 + k * 8, bdesc, idesc, acc);
+              } else {
+                const uint64_t adesc = make_kmajor_sw128_desc(a_base + g * kATile + pa_off + koff);
+                umma_f16(d_tmem, adesc, bdesc, idesc, acc);
+              }
             }
           }
           umma_commit(acc_full + a);

@@ -32,13 +32,14 @@ class LateInteractionIndex:
 
     def __init__(self, capacity_rows: int, capacity_pages: int, dtype: torch.dtype = torch.bfloat16,
                  device: Union[str, torch.device, None] = None):
-        if dtype not in _DTYPES:
-            raise NotImplementedError(f"index dtype {dtype}: bfloat16 or float16")
+        if dtype not in _DTYPES and dtype != torch.float32:
+            raise NotImplementedError(f"index dtype {dtype}: bfloat16, float16 or float32")
         self.device = resolve_device(device)
         self.dtype = dtype
         self._lib = N.load()
         self._h = C.c_void_p()
-        N.check(self._lib.lis_index_create(C.byref(self._h), self.device.index, _DTYPES[dtype],
+        code = N.LIS_F32X2 if dtype == torch.float32 else _DTYPES[dtype]   # fp32 -> two bf16 planes
+        N.check(self._lib.lis_index_create(C.byref(self._h), self.device.index, code,
                                            int(capacity_rows), int(capacity_pages)))
         self.payloads: Dict[int, Any] = {}
 
@@ -133,7 +134,9 @@ class LateInteractionIndex:
             seg_lo, seg_hi, mt_seg, seg_first = pq.table_ptrs()
             out_s = torch.empty((plan.nq, k), dtype=torch.float32, device=self.device)
             out_i = torch.empty((plan.nq, k), dtype=torch.int64, device=self.device)
-            N.check(self._lib.lis_index_search(self._h, pq.rows.data_ptr(), pq.rows.shape[0], seg_lo, seg_hi, mt_seg,
+            N.check(self._lib.lis_index_search(self._h, pq.rows.data_ptr(),
+                                               None if pq.rows_lo is None else pq.rows_lo.data_ptr(),
+                                               pq.rows.shape[0], seg_lo, seg_hi, mt_seg,
                                                plan.n_seg, plan.n_mtiles, seg_first, plan.nq, _ROUND[round_mode],
                                                int(k), out_s.data_ptr(), out_i.data_ptr(), _stream(self.device)))
         return out_s, out_i
@@ -157,10 +160,14 @@ class LateInteractionIndex:
         from .scoring import PageStore
 
         n, rows = len(self), self.num_rows
-        tok = _wrap_device(self._lib.lis_index_tokens(self._h), (rows, N.DIM), self.dtype, self.device)
+        plane = torch.bfloat16 if self.dtype == torch.float32 else self.dtype
+        tok = _wrap_device(self._lib.lis_index_tokens(self._h), (rows, N.DIM), plane, self.device)
         off = _wrap_device(self._lib.lis_index_offsets(self._h), (n + 1,), torch.int64, self.device)
         cl = _wrap_device(self._lib.lis_index_clamp(self._h), (n,), torch.uint8, self.device)
-        return PageStore(tok, off, cl, n)
+        lo = None
+        if self.dtype == torch.float32:
+            lo = _wrap_device(self._lib.lis_index_tokens_lo(self._h), (rows, N.DIM), plane, self.device)
+        return PageStore(tok, off, cl, n, lo, self.dtype)
 
 
 class _CudaArrayView:

@@ -49,7 +49,7 @@ def index_for_dataset(dataset: Sequence[dict], device=None, dtype: Optional[torc
     if len(dataset) == 0:
         raise ValueError("No passages provided")
     embs = [entry["embedding"] for entry in dataset]
-    dt = dtype or (embs[0].dtype if embs[0].dtype in (torch.bfloat16, torch.float16) else torch.bfloat16)
+    dt = dtype or (embs[0].dtype if embs[0].dtype in (torch.bfloat16, torch.float16, torch.float32) else torch.bfloat16)
     rows = sum(int(e.shape[0]) for e in embs)
     idx = LateInteractionIndex(rows, len(embs), dtype=dt, device=device)
     # torch.stack in the reference implies equal lengths; ragged lists get pad_sequence semantics

@@ -112,7 +112,8 @@ class PackedQueries:
     plan: QueryPlan
     rows: torch.Tensor      # [n_rows, 128] 16-bit, device: the queries' token rows back to back
     tables: torch.Tensor    # int32 device: seg_lo | seg_hi | mt_seg | seg_first
-    dtype: torch.dtype
+    dtype: torch.dtype      # dtype of the embeddings as given (float32 -> rows/rows_lo are bf16 planes)
+    rows_lo: Optional[torch.Tensor] = None   # low plane of split-fp32 queries
 
     def table_ptrs(self) -> Tuple[int, int, int, int]:
         p, ns, nm = self.tables.data_ptr(), self.plan.n_seg, self.plan.n_mtiles
@@ -163,12 +164,26 @@ def pack_queries(qs: TensorOrList, device: torch.device, dtype: Optional[torch.d
     if plan.n_seg == 0:
         raise ValueError("No queries provided")
     dt = dtype or flat.dtype
-    if dt not in _DTYPES:
-        raise NotImplementedError(f"query dtype {dt}: the tensor-core path takes bfloat16 or float16 embeddings")
+    if dt not in _DTYPES and dt != torch.float32:
+        raise NotImplementedError(f"query dtype {dt}: bfloat16, float16 or float32 embeddings")
     rows = flat.to(device=device, dtype=dt, non_blocking=True).contiguous()
     if rows.data_ptr() % 16:
         rows = rows.clone()
+    if dt == torch.float32:
+        hi, lo = split_f32(rows)
+        return PackedQueries(plan, hi, _device_tables(plan, device), dt, lo)
     return PackedQueries(plan, rows, _device_tables(plan, device), dt)
+
+
+def split_f32(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 [rows,128] (CUDA) -> two bf16 planes with x = hi + lo + O(2^-18 |x|) (``lis_split_f32``)."""
+    lib = N.load()
+    x = x.contiguous()
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    if x.numel():
+        N.check(lib.lis_split_f32(x.data_ptr(), x.shape[0], hi.data_ptr(), lo.data_ptr(), _stream(x.device)))
+    return hi, lo
 
 
 _TABLE_CACHE: dict = {}
@@ -191,10 +206,16 @@ def _device_tables(plan: QueryPlan, device: torch.device) -> torch.Tensor:
 @dataclass
 class PageStore:
     """Flat ragged page-token store on one device (what ``lis_maxsim_scores`` reads)."""
-    tokens: torch.Tensor            # [rows, 128] 16-bit
+    tokens: torch.Tensor            # [rows, 128] 16-bit (hi plane when the corpus is split fp32)
     offsets: torch.Tensor           # int64 [np+1]
     clamp: Optional[torch.Tensor]   # uint8 [np] or None
     n_pages: int
+    tokens_lo: Optional[torch.Tensor] = None   # lo plane of a split-fp32 corpus
+    dtype: Optional[torch.dtype] = None        # embedding dtype as given (defaults to tokens.dtype)
+
+    def __post_init__(self):
+        if self.dtype is None:
+            self.dtype = self.tokens.dtype
 
     @property
     def n_rows(self) -> int:
@@ -209,6 +230,9 @@ def build_page_store(ps: TensorOrList, device: torch.device, dtype: torch.dtype,
         tokens = ps.to(device=device, dtype=dtype, non_blocking=True).contiguous().reshape(n * s, d)
         offsets = torch.arange(0, (n + 1) * s, s, dtype=torch.int64, device=device) if s > 0 else \
             torch.zeros(n + 1, dtype=torch.int64, device=device)
+        if dtype == torch.float32:
+            hi, lo = split_f32(tokens)
+            return PageStore(hi, offsets, None, n, lo, dtype)
         return PageStore(tokens, offsets, None, n)
     pl = _as_list(ps)
     for t in pl:
@@ -223,6 +247,9 @@ def build_page_store(ps: TensorOrList, device: torch.device, dtype: torch.dtype,
     offsets = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)).to(device, non_blocking=True)
     flags = clamp_flags(lens, batch_size)
     clamp = torch.from_numpy(flags).to(device, non_blocking=True) if flags.any() else None
+    if dtype == torch.float32:
+        hi, lo = split_f32(tokens)
+        return PageStore(hi, offsets, clamp, len(pl), lo, dtype)
     return PageStore(tokens.contiguous(), offsets, clamp, len(pl))
 
 
@@ -232,8 +259,8 @@ def maxsim_scores_device(pq: PackedQueries, store: PageStore, round_mode: str = 
     lib = N.load()
     if round_mode not in _ROUND:
         raise ValueError(f"round_mode must be one of {sorted(_ROUND)}")
-    if store.tokens.dtype != pq.dtype:
-        raise ValueError(f"queries are {pq.dtype} but pages are {store.tokens.dtype}")
+    if store.dtype != pq.dtype:
+        raise ValueError(f"queries are {pq.dtype} but pages are {store.dtype}")
     device = pq.rows.device
     plan = pq.plan
     npg = store.n_pages
@@ -244,6 +271,16 @@ def maxsim_scores_device(pq: PackedQueries, store: PageStore, round_mode: str = 
         out = torch.empty((plan.nq, npg), dtype=torch.float32, device=device)
     seg_out = out if direct else torch.empty((plan.n_seg, npg), dtype=torch.float32, device=device)
     st = _stream(device)
+    if pq.dtype == torch.float32:
+        # split-fp32 planes: torch computes fp32 inputs in fp32, so there is no rounding to emulate
+        N.check(lib.lis_maxsim_scores_f32x2(pq.rows.data_ptr(), pq.rows_lo.data_ptr(), pq.rows.shape[0], seg_lo, seg_hi,
+                                            mt_seg, plan.n_seg, plan.n_mtiles, store.tokens.data_ptr(),
+                                            _ptr(store.tokens_lo), store.n_rows, store.offsets.data_ptr(),
+                                            _ptr(store.clamp), npg, seg_out.data_ptr(), seg_out.stride(0), st))
+        if not direct:
+            N.check(lib.lis_reduce_segments(seg_out.data_ptr(), seg_out.stride(0), seg_first, plan.nq, npg,
+                                            N.ROUND_F32, N.LIS_BF16, out.data_ptr(), out.stride(0), st))
+        return out
     N.check(lib.lis_maxsim_scores(pq.rows.data_ptr(), pq.rows.shape[0], seg_lo, seg_hi, mt_seg, plan.n_seg,
                                   plan.n_mtiles, store.tokens.data_ptr(), store.n_rows, store.offsets.data_ptr(),
                                   _ptr(store.clamp), npg, _DTYPES[pq.dtype], rm if direct else rm | N.ROUND_DEFER_SUM,
@@ -263,7 +300,9 @@ def score_multi_vector(qs: TensorOrList, ps: TensorOrList, batch_size: int = 128
 
     ``round_mode="reference"`` (default) reproduces what torch does to 16-bit inputs (per-token max
     and final sum rounded to the input dtype); ``"f32"`` keeps fp32 throughout (the more accurate
-    number; within 1e-4 of the fp32-widened reference).  ``batch_size`` only matters through the
+    number; within 1e-4 of the fp32-widened reference).  float32 embeddings (ColFlor's default,
+    05_experiment02.py:343-347) are scored as two bf16 planes per operand with fp32 accumulation
+    (error ~1e-6 on unit-norm rows, inside the 1e-4 bar); ``round_mode`` does not apply to them.  ``batch_size`` only matters through the
     padding it implies in the reference: a page shorter than the longest page of its block has its
     per-token max clamped at 0.  Inputs may live on any device; the corpus is not copied when it is
     already a contiguous CUDA tensor.

@@ -349,3 +349,30 @@ def test_reference_api_shapes(lis, oracle):
     assert len(ids) == 5 and all(i % 2 == 1 for i in ids)
     assert_topk_equiv(ids, [p.score for p in res.points], odd, 2e-2)
     assert all(p.payload["username"] == "ann" for p in res.points)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_fp32_embeddings_split_planes(lis, oracle):
+    """ColFlor's default dtype (05_experiment02.py:343-347): fp32 in, fp32-accurate scores out."""
+    g = torch.Generator().manual_seed(15)
+    qs = [unit(torch.randn(n, 128, generator=g)) for n in (16, 20, 150)]
+    p_lens = [int(x) for x in torch.randint(1, 300, (300,), generator=g)]
+    ps = [unit(torch.randn(n, 128, generator=g)) for n in p_lens]
+    want = oracle.score_multi_vector(qs, ps)                      # the reference's fp32 path
+    got = lis.score_multi_vector(qs, ps)
+    assert got.dtype == torch.float32 and got.shape == want.shape
+    err = (got - want).abs().max().item()
+    assert err <= TOL_F32, err
+    assert err <= 2e-5, f"split-fp32 should be ~1e-6 accurate, got {err}"
+    # padded tensor form + index form
+    pt = unit(torch.randn(64, 77, 128, generator=g))
+    qt = unit(torch.randn(5, 32, 128, generator=g))
+    want = oracle.score_multi_vector(qt, pt)
+    assert (lis.score_multi_vector(qt, pt) - want).abs().max().item() <= 2e-5
+    idx = lis.LateInteractionIndex(64 * 77, 64, dtype=torch.float32)
+    idx.add(pt)
+    assert torch.allclose(idx.read_rows(0, 77), pt[0], atol=1e-6)
+    wv, wi = oracle.topk(want, 7)
+    v, i = idx.search(qt, 7)
+    assert torch.equal(i, wi) and (v - wv).abs().max().item() <= 2e-5
+    idx.close()
