@@ -195,6 +195,16 @@ int lis_index_fill_synthetic(lis_index* idx, int64_t n, const int32_t* lens, int
 /* Copy token rows [row0, row0+n_rows) of the store to `dst` (host or device), synchronously
  * (16-bit rows; float rows hi+lo for an LIS_F32X2 index). */
 int lis_index_read_rows(const lis_index* idx, int64_t row0, int64_t n_rows, void* dst, void* stream);
+/* Raw persistence support (save / load of an index without re-ingesting):
+ *   lis_index_read_plane   copy rows [row0, row0+n_rows) of plane 0 (16-bit rows / hi) or 1 (lo) to dst
+ *   lis_index_write_rows   copy n_rows raw 16-bit rows from src (host or device) into a plane at row0
+ *   lis_index_set_tables   install the page tables (host arrays) after the rows were written:
+ *                          offsets[n_pages+1] ascending from 0, ids[n_pages] >= 0, clamp[n_pages] or NULL */
+int lis_index_read_plane(const lis_index* idx, int plane, int64_t row0, int64_t n_rows, void* dst, void* stream);
+int lis_index_write_rows(lis_index* idx, int plane, int64_t row0, int64_t n_rows, const void* src, void* stream);
+int lis_index_set_tables(lis_index* idx, const int64_t* offsets, const int64_t* ids, const uint8_t* clamp,
+                         int64_t n_pages, void* stream);
+int lis_index_dtype(const lis_index* idx);
 /* Stateless version of the generator: fill dst[n_rows,128] (device) with the rows the hash assigns
  * to global row indices row0 .. row0+n_rows-1. */
 int lis_fill_synthetic_rows(void* dst, int64_t row0, int64_t n_rows, uint64_t seed, int dtype, void* stream);

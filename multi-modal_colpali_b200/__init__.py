@@ -8,13 +8,15 @@ from .scoring import score_multi_vector, plan_queries, clamp_flags, maxsim_score
 from .index import LateInteractionIndex, topk_device, merge_topk_device
 from .head import project_normalize
 from .reference_api import (MaxSimClient, PointStruct, QueryResponse, ScoredPoint, ensure_colpali_collection,
-                            retrieve_colpali, score_results, index_for_dataset)
+                            retrieve_colpali, score_results, index_for_dataset, load_embedding_cache,
+                            create_document_embeddings, colpali_qdrant)
 from .sharded import ShardedIndex, shard_range, balanced_shard_ranges, gather_candidates
 
 __all__ = [
     "score_multi_vector", "plan_queries", "clamp_flags", "maxsim_scores_device", "pack_queries", "build_page_store",
     "LateInteractionIndex", "topk_device", "merge_topk_device", "project_normalize",
     "MaxSimClient", "PointStruct", "QueryResponse", "ScoredPoint", "ensure_colpali_collection",
-    "retrieve_colpali", "score_results", "index_for_dataset",
+    "retrieve_colpali", "score_results", "index_for_dataset", "load_embedding_cache",
+    "create_document_embeddings", "colpali_qdrant",
     "ShardedIndex", "shard_range", "balanced_shard_ranges", "gather_candidates",
 ]

@@ -63,6 +63,10 @@ SIGNATURES = {
     "lis_index_clamp": (_vp, [_vp]),
     "lis_index_fill_synthetic": (_i32, [_vp, _i64, _vp, _i32, C.c_uint64, _i64, _vp]),
     "lis_index_read_rows": (_i32, [_vp, _i64, _i64, _vp, _vp]),
+    "lis_index_read_plane": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp]),
+    "lis_index_write_rows": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp]),
+    "lis_index_set_tables": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "lis_index_dtype": (_i32, [_vp]),
     "lis_fill_synthetic_rows": (_i32, [_vp, _i64, _i64, C.c_uint64, _i32, _vp]),
     "lis_index_search": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
 }

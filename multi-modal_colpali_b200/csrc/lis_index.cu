@@ -285,6 +285,57 @@ int lis_index_read_rows(const lis_index* ix, int64_t row0, int64_t n_rows, void*
   return LIS_OK;
 }
 
+int lis_index_dtype(const lis_index* ix) { return ix ? ix->dtype : -1; }
+
+int lis_index_read_plane(const lis_index* ix, int plane, int64_t row0, int64_t n_rows, void* dst, void* stream) {
+  LIS_REQUIRE(ix && dst, "null pointer");
+  LIS_REQUIRE(plane == 0 || (plane == 1 && ix->dtype == LIS_F32X2), "no such plane");
+  LIS_REQUIRE(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= ix->n_rows, "row range out of bounds");
+  if (n_rows == 0) return LIS_OK;
+  const uint8_t* base = plane ? lo_plane(ix) : static_cast<const uint8_t*>(ix->tokens);
+  cudaStream_t st = (cudaStream_t)stream;
+  LIS_CUDA_CHECK(cudaMemcpyAsync(dst, base + row0 * 256, (size_t)n_rows * 256, cudaMemcpyDefault, st));
+  LIS_CUDA_CHECK(cudaStreamSynchronize(st));
+  return LIS_OK;
+}
+
+int lis_index_write_rows(lis_index* ix, int plane, int64_t row0, int64_t n_rows, const void* src, void* stream) {
+  LIS_REQUIRE(ix && src, "null pointer");
+  LIS_REQUIRE(plane == 0 || (plane == 1 && ix->dtype == LIS_F32X2), "no such plane");
+  LIS_REQUIRE(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= ix->cap_rows, "row range exceeds capacity");
+  if (n_rows == 0) return LIS_OK;
+  uint8_t* base = plane ? lo_plane(ix) : static_cast<uint8_t*>(ix->tokens);
+  cudaStream_t st = (cudaStream_t)stream;
+  LIS_CUDA_CHECK(cudaSetDevice(ix->device));
+  LIS_CUDA_CHECK(cudaMemcpyAsync(base + row0 * 256, src, (size_t)n_rows * 256, cudaMemcpyDefault, st));
+  LIS_CUDA_CHECK(cudaStreamSynchronize(st));
+  return LIS_OK;
+}
+
+int lis_index_set_tables(lis_index* ix, const int64_t* offsets, const int64_t* ids, const uint8_t* clamp,
+                         int64_t n_pages, void* stream) {
+  LIS_REQUIRE(ix && offsets && ids, "null pointer");
+  LIS_REQUIRE(n_pages >= 0 && n_pages <= ix->cap_pages, "page count exceeds capacity");
+  LIS_REQUIRE(offsets[0] == 0, "offsets must start at 0");
+  for (int64_t i = 0; i < n_pages; ++i) {
+    LIS_REQUIRE(offsets[i + 1] >= offsets[i], "offsets must be ascending (page %lld)", (long long)i);
+    LIS_REQUIRE(ids[i] >= 0, "page ids must be non-negative");
+  }
+  LIS_REQUIRE(offsets[n_pages] <= ix->cap_rows, "rows exceed capacity");
+  cudaStream_t st = (cudaStream_t)stream;
+  LIS_CUDA_CHECK(cudaSetDevice(ix->device));
+  LIS_CUDA_CHECK(cudaMemcpyAsync(ix->offsets, offsets, (size_t)(n_pages + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (n_pages > 0) {
+    LIS_CUDA_CHECK(cudaMemcpyAsync(ix->ids, ids, (size_t)n_pages * 8, cudaMemcpyHostToDevice, st));
+    if (clamp) LIS_CUDA_CHECK(cudaMemcpyAsync(ix->clamp, clamp, (size_t)n_pages, cudaMemcpyHostToDevice, st));
+    else LIS_CUDA_CHECK(cudaMemsetAsync(ix->clamp, 0, (size_t)n_pages, st));
+  }
+  LIS_CUDA_CHECK(cudaStreamSynchronize(st));
+  ix->n_pages = n_pages;
+  ix->n_rows = offsets[n_pages];
+  return LIS_OK;
+}
+
 int lis_index_search(lis_index* ix, const void* q, const void* q_lo, int64_t q_rows, const int32_t* seg_lo, const int32_t* seg_hi,
                      const int32_t* mt_seg, int64_t n_seg, int64_t n_mtiles, const int32_t* seg_first, int64_t nq,
                      int round_mode, int k, float* out_scores, int64_t* out_ids, void* stream) {

@@ -119,6 +119,78 @@ class LateInteractionIndex:
             N.check(self._lib.lis_index_read_rows(self._h, int(row0), int(n_rows), out.data_ptr(), _stream(self.device)))
         return out
 
+    # -- persistence ------------------------------------------------------------------------------
+    _CHUNK_ROWS = 1 << 22   # 1 GiB of 16-bit rows per copy
+
+    def page_tables(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """(offsets int64 [n+1], ids int64 [n], clamp uint8 [n]) copied to the host."""
+        st = self._as_store()
+        ids = _wrap_device(self._lib.lis_index_ids(self._h), (len(self),), torch.int64, self.device)
+        return st.offsets.cpu().numpy(), ids.cpu().numpy(), st.clamp.cpu().numpy()
+
+    def save(self, path) -> None:
+        """Write the index to a directory: ``meta.json``, raw row planes (``tokens.bin`` [+ ``tokens_lo.bin``]),
+        ``offsets.npy`` / ``ids.npy`` / ``clamp.npy`` and ``payloads.pkl``.  The row files are exactly the HBM
+        layout, so loading is a straight copy (memory-mapped, chunked) with no re-encoding."""
+        import json
+        import pickle
+        from pathlib import Path
+
+        d = Path(path)
+        d.mkdir(parents=True, exist_ok=True)
+        n, rows = len(self), self.num_rows
+        off, ids, clamp = self.page_tables() if n else (np.zeros(1, np.int64), np.zeros(0, np.int64), np.zeros(0, np.uint8))
+        np.save(d / "offsets.npy", off); np.save(d / "ids.npy", ids); np.save(d / "clamp.npy", clamp)
+        planes = 2 if self.dtype == torch.float32 else 1
+        with torch.cuda.device(self.device):
+            for pl in range(planes):
+                with open(d / ("tokens_lo.bin" if pl else "tokens.bin"), "wb") as f:
+                    for r0 in range(0, rows, self._CHUNK_ROWS):
+                        nr = min(self._CHUNK_ROWS, rows - r0)
+                        buf = torch.empty((nr, N.DIM), dtype=torch.int16)
+                        N.check(self._lib.lis_index_read_plane(self._h, pl, r0, nr, buf.data_ptr(), _stream(self.device)))
+                        f.write(buf.numpy().tobytes())
+        with open(d / "payloads.pkl", "wb") as f:
+            pickle.dump(self.payloads, f)
+        (d / "meta.json").write_text(json.dumps({
+            "format": "lis-index-v1", "dtype": str(self.dtype).split(".")[-1], "n_pages": n, "n_rows": rows, "dim": N.DIM,
+            "planes": planes}))
+
+    @classmethod
+    def load(cls, path, device=None, capacity_rows: Optional[int] = None, capacity_pages: Optional[int] = None
+             ) -> "LateInteractionIndex":
+        """Inverse of :meth:`save`; capacities default to the stored sizes (pass larger ones to keep adding)."""
+        import json
+        import pickle
+        from pathlib import Path
+
+        d = Path(path)
+        meta = json.loads((d / "meta.json").read_text())
+        if meta.get("format") != "lis-index-v1" or meta.get("dim") != N.DIM:
+            raise ValueError(f"{d} is not a lis-index-v1 directory")
+        dtype = getattr(torch, meta["dtype"])
+        n, rows = int(meta["n_pages"]), int(meta["n_rows"])
+        idx = cls(max(capacity_rows or rows, rows, 1), max(capacity_pages or n, n, 1), dtype=dtype, device=device)
+        with torch.cuda.device(idx.device):
+            for pl in range(int(meta["planes"])):
+                if rows == 0:
+                    break
+                mm = np.memmap(d / ("tokens_lo.bin" if pl else "tokens.bin"), dtype=np.int16, mode="r", shape=(rows, N.DIM))
+                for r0 in range(0, rows, cls._CHUNK_ROWS):
+                    nr = min(cls._CHUNK_ROWS, rows - r0)
+                    chunk = np.ascontiguousarray(mm[r0:r0 + nr])
+                    N.check(idx._lib.lis_index_write_rows(idx._h, pl, r0, nr, chunk.ctypes.data, _stream(idx.device)))
+            off = np.ascontiguousarray(np.load(d / "offsets.npy"), dtype=np.int64)
+            ids = np.ascontiguousarray(np.load(d / "ids.npy"), dtype=np.int64)
+            clamp = np.ascontiguousarray(np.load(d / "clamp.npy"), dtype=np.uint8)
+            if len(off) != n + 1 or len(ids) != n or len(clamp) != n or (n and off[-1] != rows):
+                raise ValueError(f"{d}: page tables are inconsistent with meta.json")
+            N.check(idx._lib.lis_index_set_tables(idx._h, off.ctypes.data, ids.ctypes.data if n else None,
+                                                  clamp.ctypes.data if n else None, n, _stream(idx.device)) if n else 0)
+        with open(d / "payloads.pkl", "rb") as f:
+            idx.payloads = pickle.load(f)
+        return idx
+
     # -- search -----------------------------------------------------------------------------------
     def search_device(self, qs: TensorOrList, k: int, round_mode: str = "f32") -> Tuple[torch.Tensor, torch.Tensor]:
         """MaxSim + top-k entirely on the device; returns device tensors (scores fp32 [nq,k], ids int64 [nq,k])."""

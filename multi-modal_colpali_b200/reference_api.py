@@ -62,6 +62,64 @@ def index_for_dataset(dataset: Sequence[dict], device=None, dtype: Optional[torc
     return idx
 
 
+def load_embedding_cache(path: str) -> List[dict]:
+    """Load the reference's page-embedding cache ``data/<retriever>_pdf_emb.pkl`` (05_experiment02.py:391-398):
+    a pickled ``list[dict{embedding, doc_id, page_id, file_name}]``.  Feed the result to
+    :func:`score_results` / :func:`index_for_dataset` unchanged."""
+    import pickle
+
+    with open(path, "rb") as f:
+        dataset = pickle.load(f)
+    if not isinstance(dataset, list) or (dataset and "embedding" not in dataset[0]):
+        raise ValueError(f"{path} is not a page-embedding cache (list of dicts with an 'embedding' entry)")
+    return dataset
+
+
+def create_document_embeddings(images_per_pdf: dict, model, processor, batch_size: int = 2) -> List[dict]:
+    """functions.py:765-809 from already rendered pages (``{file_name: [PIL images]}`` -- what the reference's
+    ``convert_pdf_dir_to_images`` returns; PDF rendering itself is out of scope).  Same list-of-dicts result."""
+    all_embeddings: List[dict] = []
+    for doc_idx, (filename, images) in enumerate(images_per_pdf.items()):
+        page_counter = 0
+        for i in range(0, len(images), batch_size):
+            batch = processor.process_images(images[i:i + batch_size])
+            with torch.no_grad():
+                inputs = {k: v.to(model.device) for k, v in batch.items()}
+                batch_embeddings = _embeddings_of(model(**inputs))
+            for embedding in torch.unbind(batch_embeddings.to("cpu")):
+                all_embeddings.append({"embedding": embedding, "doc_id": doc_idx, "page_id": page_counter,
+                                       "file_name": filename})
+                page_counter += 1
+    return all_embeddings
+
+
+def colpali_qdrant(dataset, papers, doi, model, processor, qdrant_client, qdrant_collection, batch_size=4):
+    """functions.py:827-873: encode page images in batches and upsert them with the reference's payload.
+    With a :class:`MaxSimClient` the embedding tensors go to the index directly (no ``tolist()`` round trip)."""
+    direct = isinstance(qdrant_client, MaxSimClient)
+    for i in range(0, len(dataset), batch_size):
+        batch = dataset[i:i + batch_size]
+        images = [item["image"] for item in batch]
+        with torch.no_grad():
+            batch_images = processor.process_images(images).to(model.device)
+            image_embeddings = _embeddings_of(model(**batch_images))
+        points = []
+        for j, embedding in enumerate(image_embeddings):
+            links = [d for paper, d in zip(papers, doi) if paper.split("/")[-1] == batch[j]["filename"]]
+            points.append(PointStruct(
+                id=str(uuid.uuid4()),
+                vector=embedding if direct else embedding.tolist(),
+                payload={"document_name": batch[j]["filename"], "document_id": str(uuid.uuid4()),
+                         "document_link": links[0] if links else "", "type": "pdf_page", "page_no": batch[j]["page_no"],
+                         "ref": "", "caption": "", "img_link": batch[j]["img_link"]}))
+        try:
+            qdrant_client.upsert(collection_name=qdrant_collection, points=points)
+        except Exception as e:  # the reference skips the batch and carries on (functions.py:866-868)
+            print(f"Error during upsert: {e}")
+            continue
+    print("Indexing complete!")
+
+
 def score_results(queries: List[str], processor, model, dataset: List[dict], images_per_pdf: dict,
                   top_k: int) -> List[List[dict]]:
     """Retrieve top-k pages per query with late-interaction scoring (05_experiment02.py:200-236)."""

@@ -377,3 +377,69 @@ def test_fp32_embeddings_split_planes(lis, oracle):
     v, i = idx.search(qt, 7)
     assert torch.equal(i, wi) and (v - wv).abs().max().item() <= 2e-6 * want.abs().max().item()
     idx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_index_save_load_roundtrip(lis, oracle, tmp_path, dtype):
+    g = torch.Generator().manual_seed(16)
+    ps = [unit(torch.randn(int(n), 128, generator=g)).to(dtype) for n in torch.randint(1, 90, (120,), generator=g)]
+    qs = [unit(torch.randn(12, 128, generator=g)).to(dtype), unit(torch.randn(31, 128, generator=g)).to(dtype)]
+    idx = lis.LateInteractionIndex(sum(p.shape[0] for p in ps), len(ps), dtype=dtype)
+    idx.add(ps, ids=[7 * i + 3 for i in range(len(ps))], payloads=[{"page_no": i} for i in range(len(ps))],
+            zero_pad_block=128)
+    v0, i0 = idx.search(qs, 9)
+    idx.save(tmp_path / "ix")
+    idx.close()
+    back = lis.LateInteractionIndex.load(tmp_path / "ix", capacity_rows=20000, capacity_pages=200)
+    assert len(back) == len(ps) and back.dtype == dtype and back.payloads[7 * 5 + 3] == {"page_no": 5}
+    v1, i1 = back.search(qs, 9)
+    assert torch.equal(i0, i1) and torch.equal(v0, v1)
+    back.add(ps[:3], ids=[9001, 9002, 9003])              # still appendable after a load
+    assert len(back) == len(ps) + 3
+    back.close()
+
+
+class _ImgProcessor:
+    """process_images: a "page image" here is just an int seed; returns a dict batch like a HF processor."""
+
+    def process_images(self, images):
+        return _FakeBatch(seeds=torch.tensor(images))
+
+
+class _ImgModel:
+    device = torch.device("cuda", 0)
+
+    def __call__(self, seeds):
+        out = [unit(torch.randn(40, 128, generator=torch.Generator().manual_seed(int(s)))) for s in seeds.tolist()]
+        return torch.stack(out).to(torch.bfloat16).cuda()
+
+
+def test_ingestion_dropins(lis, oracle, tmp_path):
+    import pickle
+
+    model, proc = _ImgModel(), _ImgProcessor()
+    images_per_pdf = {"a.pdf": [1, 2, 3], "b.pdf": [4, 5]}
+    ds = lis.create_document_embeddings(images_per_pdf, model, proc, batch_size=2)
+    assert [(e["doc_id"], e["page_id"], e["file_name"]) for e in ds] == \\
+        [(0, 0, "a.pdf"), (0, 1, "a.pdf"), (0, 2, "a.pdf"), (1, 0, "b.pdf"), (1, 1, "b.pdf")]
+    assert all(e["embedding"].device.type == "cpu" and e["embedding"].shape == (40, 128) for e in ds)
+    with open(tmp_path / "emb.pkl", "wb") as f:           # the reference's cache format (05_experiment02.py:391-398)
+        pickle.dump(ds, f)
+    ds2 = lis.load_embedding_cache(str(tmp_path / "emb.pkl"))
+    table = {"q": unit(torch.randn(10, 128, generator=torch.Generator().manual_seed(9))).to(torch.bfloat16)}
+    res = lis.score_results(["q"], _FakeProcessor(table), _FakeModel(), ds2, {"a.pdf": "ABC", "b.pdf": "DE"}, top_k=3)
+    want = oracle.score_multi_vector(table["q"][None], torch.stack([e["embedding"] for e in ds]))[0]
+    assert_topk_equiv([{"a.pdf": 0, "b.pdf": 3}[r["file_name"]] + r["page_id"] for r in res[0]],
+                      [r["score"] for r in res[0]], want, TOL_BF16)
+
+    client = lis.MaxSimClient(capacity_rows=4096, capacity_pages=64)
+    lis.ensure_colpali_collection(client, "pages")
+    pages = [{"image": s, "filename": "a.pdf" if s <= 3 else "b.pdf", "page_no": s, "img_link": f"img{s}"} for s in range(1, 6)]
+    lis.colpali_qdrant(pages, ["x/a.pdf", "y/b.pdf"], ["doi:a", "doi:b"], model, proc, client, "pages", batch_size=2)
+    assert client.count("pages") == 5
+    out = client.query_points("pages", query=table["q"], limit=5)
+    assert len(out.points) == 5 and out.points[0].payload["type"] == "pdf_page"
+    assert {p.payload["document_link"] for p in out.points} == {"doi:a", "doi:b"}
+    best = out.points[0]
+    assert best.payload["page_no"] == int(torch.argmax(want).item()) + 1

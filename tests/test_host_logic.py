@@ -79,3 +79,16 @@ def test_filter_parsing():
         def __init__(self, must): self.must = must
 
     assert api._filter_conditions(F([FC("username", MV("bob"))])) == [("username", "bob")]
+
+
+def test_embedding_cache_loader_validates(lis, tmp_path):
+    import pickle
+
+    good = [{"embedding": torch.zeros(3, 128), "doc_id": 0, "page_id": 0, "file_name": "a.pdf"}]
+    with open(tmp_path / "ok.pkl", "wb") as f:
+        pickle.dump(good, f)
+    assert lis.load_embedding_cache(str(tmp_path / "ok.pkl"))[0]["file_name"] == "a.pdf"
+    with open(tmp_path / "bad.pkl", "wb") as f:
+        pickle.dump({"not": "a list"}, f)
+    with pytest.raises(ValueError):
+        lis.load_embedding_cache(str(tmp_path / "bad.pkl"))
