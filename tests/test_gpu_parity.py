@@ -421,8 +421,8 @@ def test_ingestion_dropins(lis, oracle, tmp_path):
     model, proc = _ImgModel(), _ImgProcessor()
     images_per_pdf = {"a.pdf": [1, 2, 3], "b.pdf": [4, 5]}
     ds = lis.create_document_embeddings(images_per_pdf, model, proc, batch_size=2)
-    assert [(e["doc_id"], e["page_id"], e["file_name"]) for e in ds] == \\
-        [(0, 0, "a.pdf"), (0, 1, "a.pdf"), (0, 2, "a.pdf"), (1, 0, "b.pdf"), (1, 1, "b.pdf")]
+    assert [(e["doc_id"], e["page_id"], e["file_name"]) for e in ds] == [
+        (0, 0, "a.pdf"), (0, 1, "a.pdf"), (0, 2, "a.pdf"), (1, 0, "b.pdf"), (1, 1, "b.pdf")]
     assert all(e["embedding"].device.type == "cpu" and e["embedding"].shape == (40, 128) for e in ds)
     with open(tmp_path / "emb.pkl", "wb") as f:           # the reference's cache format (05_experiment02.py:391-398)
         pickle.dump(ds, f)
