@@ -125,6 +125,9 @@ int lis_reduce_segments(const float* seg_scores, int64_t ld_seg, const int32_t* 
  *   epi_halves {0, 1, 2}           4 or 8 epilogue warps
  *   a_operand  {0, 1, 2}           query operand of the MMA in shared memory (1) or tensor memory (2) */
 int lis_set_tuning(int tile_n, int group, int max_ctas, int epi_halves, int a_operand);
+/* Timing experiments only (scores become invalid): 1 = K1's epilogue skips the TMEM read-out, 2 = it skips
+ * the max arithmetic; 0 restores normal operation.  Used by scripts/gpu_ablate.py to attribute time. */
+int lis_set_ablation(int mode);
 /* Number of kernels this library launched since load (all entry points). */
 int64_t lis_launch_count(void);
 

@@ -22,6 +22,7 @@ struct Tuning {
   int max_ctas = 0;
   int epi_halves = 0;  // 0 = auto
   int a_operand = 0;   // 0 = auto, 1 = shared memory (SS), 2 = tensor memory (TS)
+  int ablate = 0;      // timing experiments only
 };
 extern Tuning g_tuning;
 

@@ -153,6 +153,11 @@ extern "C" {
 const char* lis_last_error(void) { return g_err; }
 int lis_abi_version(void) { return LIS_ABI_VERSION; }
 int64_t lis_launch_count(void) { return g_launches.load(); }
+int lis_set_ablation(int mode) {
+  LIS_REQUIRE(mode >= 0 && mode <= 2, "ablation mode must be 0, 1 or 2");
+  g_tuning.ablate = mode;
+  return LIS_OK;
+}
 
 int lis_device_supported(int device) {
   int major = 0;
@@ -362,6 +367,7 @@ static int maxsim_impl(const void* q, const void* q_lo, int64_t q_rows, const in
     a.n_mt = (int32_t)std::min<int64_t>(g, n_mtiles - mt0);
     a.round_mode = round_mode;
     a.is_bf16 = dtype == LIS_BF16;
+    a.ablate = g_tuning.ablate;
     // the instantiation whose group equals this pass's tile count (the last pass may be short)
     rc = dispatch_maxsim(nt, a.n_mt, atm, m, a, grid, st, false, planes);
     if (rc) return rc;
@@ -456,6 +462,7 @@ int lis_debug_sim_tile(const void* q, int64_t q_rows, const void* tokens, int64_
   a.p_offsets = off; a.p_clamp = nullptr; a.seg_lo = seg_lo; a.seg_hi = seg_hi; a.mt_seg = mt_seg;
   a.out = dummy; a.dbg = out; a.ld_out = 1; a.np = 1; a.mt0 = 0; a.n_mt = 1; a.round_mode = 0;
   a.is_bf16 = dtype == LIS_BF16;
+  a.ablate = 0;
   a.q = q;
   a.q_rows = q_rows;
   rc = dispatch_maxsim(tile_n, 1, a_in_tmem != 0, m, a, 1, st, true);

@@ -47,6 +47,7 @@ struct MaxSimArgs {
   int32_t n_mt;       // M tiles in this launch (1..G)
   int32_t round_mode; // lis_round_mode bits
   int32_t is_bf16;    // 1 = bf16, 0 = fp16
+  int32_t ablate;     // timing experiments only (results invalid): 1 = epilogue skips TMEM loads, 2 = skips the max
 };
 
 __device__ __forceinline__ float round_to_input_dtype(float x, int is_bf16) {
@@ -175,8 +176,8 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0 && pa < pb) {
-      if (!ATM && ntiles > 0) {
+    if (pa < pb) {
+      if (!ATM && ntiles > 0 && elect_one_sync()) {
         mbar_arrive_expect_tx(q_full, (uint32_t)n_mt * kATile);
         for (int g = 0; g < n_mt; ++g)
           for (int pl = 0; pl < P; ++pl)
@@ -184,23 +185,30 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
               tma_load_2d(smem_a + g * kATile + pl * kATileBytes + h * (kMTile * 128), pl ? &tmap_q2 : &tmap_q,
                           q_full, h * kKHalf, (args.mt0 + g) * kMTile, kPolicyEvictLast);
       }
+      __syncwarp();
       for (int t = 0; t < ntiles; ++t) {
         const int s = t % NS;
         const uint32_t ph = (uint32_t)(t / NS) & 1u;
         mbar_wait(b_empty + s, ph ^ 1u);
-        mbar_arrive_expect_tx(b_full + s, kBStageBytes);
-        uint8_t* dst = smem_b + (size_t)s * kBStageBytes;
-        const int32_t r = (int32_t)(row0 + (int64_t)t * NT);
-        for (int pl = 0; pl < P; ++pl) {
-          const CUtensorMap* tm = pl ? &tmap_p2 : &tmap_p;
-          tma_load_2d(dst + pl * kBPlaneBytes, tm, b_full + s, 0, r, kPolicyEvictFirst);
-          tma_load_2d(dst + pl * kBPlaneBytes + kBHalfBytes, tm, b_full + s, kKHalf, r, kPolicyEvictFirst);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(b_full + s, kBStageBytes);
+          uint8_t* dst = smem_b + (size_t)s * kBStageBytes;
+          const int32_t r = (int32_t)(row0 + (int64_t)t * NT);
+          for (int pl = 0; pl < P; ++pl) {
+            const CUtensorMap* tm = pl ? &tmap_p2 : &tmap_p;
+            tma_load_2d(dst + pl * kBPlaneBytes, tm, b_full + s, 0, r, kPolicyEvictFirst);
+            tma_load_2d(dst + pl * kBPlaneBytes + kBHalfBytes, tm, b_full + s, kKHalf, r, kPolicyEvictFirst);
+          }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && pa < pb && ntiles > 0) {
+    // The whole warp runs the loop converged and one elected lane issues: in that form ptxas keeps
+    // the (warp-uniform) descriptors in uniform registers; issuing from an `if (lane == 0)` branch
+    // costs ~85 cycles per tcgen05.mma instead of ~50 (profiles/micro_mma_rate_r1.txt).
+    if (pa < pb && ntiles > 0) {
       const uint32_t idesc = make_idesc_f16(args.is_bf16 ? 1u : 0u, kMTile, NT);
       const uint32_t a_base = smem_u32(smem_a);
       const uint32_t b_base = smem_u32(smem_b);
@@ -215,29 +223,32 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           mbar_wait(acc_empty + a, ((use / NACC) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + kACols + a * NT;
-          // plane pairs (A plane, B plane): hi*hi only, or hi*hi + hi*lo + lo*hi for split fp32
+          if (elect_one_sync()) {
+            // plane pairs (A plane, B plane): hi*hi only, or hi*hi + hi*lo + lo*hi for split fp32
 #pragma unroll
-          for (int pp = 0; pp < (P == 2 ? 3 : 1); ++pp) {
-            const uint32_t pa_off = (pp == 2 ? 1u : 0u) * kATileBytes;
-            const uint32_t pb_off = (pp == 1 ? 1u : 0u) * kBPlaneBytes;
+            for (int pp = 0; pp < (P == 2 ? 3 : 1); ++pp) {
+              const uint32_t pa_off = (pp == 2 ? 1u : 0u) * kATileBytes;
+              const uint32_t pb_off = (pp == 1 ? 1u : 0u) * kBPlaneBytes;
 #pragma unroll
-            for (int k = 0; k < kDim / 16; ++k) {
-              const uint32_t koff = (uint32_t)(k >> 2) * (kMTile * 128) + (uint32_t)(k & 3) * 32;
-              const uint32_t koff_b = (uint32_t)(k >> 2) * kBHalfBytes + (uint32_t)(k & 3) * 32;
-              const uint64_t bdesc = make_kmajor_sw128_desc(b_base + s * kBStageBytes + pb_off + koff_b);
-              const uint32_t acc = (pp | k) ? 1u : 0u;
-              if (ATM) {
-                // 16 K-elements of a 16-bit operand = 8 TMEM columns per k-step
-                umma_f16_ts(d_tmem, tmem_base + g * 64 + k * 8, bdesc, idesc, acc);
-              } else {
-                const uint64_t adesc = make_kmajor_sw128_desc(a_base + g * kATile + pa_off + koff);
-                umma_f16(d_tmem, adesc, bdesc, idesc, acc);
+              for (int k = 0; k < kDim / 16; ++k) {
+                const uint32_t koff = (uint32_t)(k >> 2) * (kMTile * 128) + (uint32_t)(k & 3) * 32;
+                const uint32_t koff_b = (uint32_t)(k >> 2) * kBHalfBytes + (uint32_t)(k & 3) * 32;
+                const uint64_t bdesc = make_kmajor_sw128_desc(b_base + s * kBStageBytes + pb_off + koff_b);
+                const uint32_t acc = (pp | k) ? 1u : 0u;
+                if (ATM) {
+                  // 16 K-elements of a 16-bit operand = 8 TMEM columns per k-step
+                  umma_f16_ts(d_tmem, tmem_base + g * 64 + k * 8, bdesc, idesc, acc);
+                } else {
+                  const uint64_t adesc = make_kmajor_sw128_desc(a_base + g * kATile + pa_off + koff);
+                  umma_f16(d_tmem, adesc, bdesc, idesc, acc);
+                }
               }
             }
+            umma_commit(acc_full + a);
+            if (g == n_mt - 1) umma_commit(b_empty + s);
           }
-          umma_commit(acc_full + a);
+          __syncwarp();
         }
-        umma_commit(b_empty + s);
       }
     }
   } else {
@@ -389,11 +400,13 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           for (int grp = 0; grp < NOWN / GRP; ++grp) {
             uint32_t v0[32], v1[32], v2[32], v3[32];
             const uint32_t ta = taddr + grp * GRP * 32;
-            tmem_ld32(ta, v0);
-            if (GRP > 1) tmem_ld32(ta + 32, v1);
-            if (GRP > 2) tmem_ld32(ta + 64, v2);
-            if (GRP > 3) tmem_ld32(ta + 96, v3);
-            tmem_ld_wait();
+            if (args.ablate != 1) {
+              tmem_ld32(ta, v0);
+              if (GRP > 1) tmem_ld32(ta + 32, v1);
+              if (GRP > 2) tmem_ld32(ta + 64, v2);
+              if (GRP > 3) tmem_ld32(ta + 96, v3);
+              tmem_ld_wait();
+            }
             if (grp == NOWN / GRP - 1) {
               tc_fence_before();
               __syncwarp();
@@ -403,7 +416,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             if (grp == 0 && EH == 2 && half == 1) skip_to(c_lo * 32);
             if (!DBG && (!live || pe > cb + GRP * 32)) {
               // fast path: no page ends inside these columns
-              if (live) {
+              if (live && args.ablate == 0) {
                 m = max32(v0, m);
                 if (GRP > 1) m = max32(v1, m);
                 if (GRP > 2) m = max32(v2, m);

@@ -6,7 +6,7 @@
 #include "../../multi-modal_colpali_b200/csrc/lis_ptx.cuh"
 using namespace lis;
 
-template <int N>
+template <int N, bool TS, bool ELECT>
 __global__ void __launch_bounds__(128, 1) mma_rate(int groups, long long* cycles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[4];
@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate(int groups, long long* cycles
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = slot;
-  if (threadIdx.x == 32) {
+  if (ELECT ? (warp == 1) : (threadIdx.x == 32)) {
     const uint32_t idesc = make_idesc_f16(1, 128, N);
     const uint32_t a_base = smem_u32(smem);
     const uint32_t b_base = a_base + 96 * 1024;
@@ -32,38 +32,40 @@ __global__ void __launch_bounds__(128, 1) mma_rate(int groups, long long* cycles
     for (int g = 0; g < groups; ++g) {
       const uint32_t a = a_base + (g % 3) * 32768;
       const uint32_t b = b_base + ((g / 3) & 1) * (N * 256);
-      const uint32_t d = tmem + (g & 1) * N;
+      const uint32_t d = tmem + (TS ? 192 : 0) + (g & 1) * N;
       if (g >= 2) mbar_wait(bars + (g & 1), ((g - 2) >> 1) & 1);
+      if (ELECT) { if (!elect_one_sync()) continue; }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const uint32_t ka = (k >> 2) * 16384 + (k & 3) * 32;
         const uint32_t kb = (k >> 2) * (N * 128) + (k & 3) * 32;
-        umma_f16(d, make_kmajor_sw128_desc(a + ka), make_kmajor_sw128_desc(b + kb), idesc, k > 0);
+        if (TS) umma_f16_ts(d, tmem + (g % 3) * 64 + k * 8, make_kmajor_sw128_desc(b + kb), idesc, k > 0);
+        else umma_f16(d, make_kmajor_sw128_desc(a + ka), make_kmajor_sw128_desc(b + kb), idesc, k > 0);
       }
       umma_commit(bars + (g & 1));
     }
     mbar_wait(bars + ((groups - 1) & 1), ((groups - 1) >> 1) & 1);
     const long long t1 = clock64();
-    cycles[blockIdx.x] = t1 - t0;
+    if ((threadIdx.x & 31) == 0) cycles[blockIdx.x] = t1 - t0;
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-template <int N>
+template <int N, bool TS, bool ELECT>
 void run() {
   long long* d;
   cudaMalloc(&d, 148 * 8);
   const int smem = (96 + 128) * 1024;
-  cudaFuncSetAttribute(mma_rate<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(mma_rate<N, TS, ELECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int groups = 20000;
-  mma_rate<N><<<148, 128, smem>>>(groups, d);
-  mma_rate<N><<<148, 128, smem>>>(groups, d);
+  mma_rate<N, TS, ELECT><<<148, 128, smem>>>(groups, d);
+  mma_rate<N, TS, ELECT><<<148, 128, smem>>>(groups, d);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
-  mma_rate<N><<<148, 128, smem>>>(groups, d);
+  mma_rate<N, TS, ELECT><<<148, 128, smem>>>(groups, d);
   cudaEventRecord(e1);
   cudaError_t e = cudaDeviceSynchronize();
   float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -72,9 +74,13 @@ void run() {
   double avg = 0; for (int i = 0; i < 148; ++i) avg += h[i]; avg /= 148;
   const double per_mma = avg / (groups * 8.0);
   const double flops = 148.0 * groups * 8 * 2.0 * 128 * N * 16;
-  printf("N=%3d cycles/MMA=%6.1f (ideal %d)  util=%.3f  wall %.3f ms -> %.1f TFLOP/s, eff clock %.0f MHz  (%s)\n", N, per_mma, N / 2,
+  printf("%s N=%3d cycles/MMA=%6.1f (ideal %d)  util=%.3f  wall %.3f ms -> %.1f TFLOP/s, eff clock %.0f MHz  (%s)\n", ELECT ? (TS ? "TS/elect" : "SS/elect") : (TS ? "TS/lane0" : "SS/lane0"), N, per_mma, N / 2,
          (N / 2) / per_mma, ms, flops / (ms * 1e-3) / 1e12, avg / (ms * 1e-3) / 1e6, cudaGetErrorString(e));
   cudaFree(d);
 }
 
-int main() { run<256>(); run<128>(); run<256>(); return 0; }
+int main() {
+  run<256, false, false>(); run<128, false, false>(); run<64, true, false>();
+  run<256, false, true>(); run<128, false, true>(); run<128, true, true>(); run<64, true, true>(); run<32, true, true>();
+  return 0;
+}
