@@ -10,7 +10,7 @@ import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-_LIB_PATH = _PKG / "_lib" / "liblis.so"
+_LIB_PATH = Path(os.environ["LIS_LIB"]) if os.environ.get("LIS_LIB") else _PKG / "_lib" / "liblis.so"  # LIS_LIB: A/B builds
 
 LIS_OK = 0
 LIS_E_INVALID = -1

@@ -39,6 +39,27 @@ def _stale() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
+def build_variant(name: str, defines) -> Path:
+    """Experiment builds: ``_lib/liblis_<name>.so`` with extra -D flags (select with LIS_LIB=...)."""
+    nvcc = _nvcc()
+    objdir = LIBDIR / f"obj_{name}"
+    objdir.mkdir(parents=True, exist_ok=True)
+    objs = []
+    for src in SOURCES:
+        obj = objdir / src.replace(".cu", ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", str(CSRC / src), "-o", str(obj)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stderr}")
+        objs.append(obj)
+    out = LIBDIR / f"liblis_{name}.so"
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *map(str, objs)],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stderr}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every CUDA source for sm_100a and link ``liblis.so``.  Returns the library path."""
     if not force and not _stale():

@@ -21,6 +21,13 @@
 #pragma once
 #include "lis_ptx.cuh"
 
+// A/B experiments: -DLIS_MMA_ISSUE_LANE0 issues the MMAs from `lane == 0` instead of an elected lane.
+#ifdef LIS_MMA_ISSUE_LANE0
+#define LIS_ISSUE_PRED (lane == 0)
+#else
+#define LIS_ISSUE_PRED elect_one_sync()
+#endif
+
 namespace lis {
 
 constexpr int kDim = 128;        // embedding width (VECTOR_SIZE, 01_create_context_qdrant.py:70)
@@ -223,7 +230,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           mbar_wait(acc_empty + a, ((use / NACC) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + kACols + a * NT;
-          if (elect_one_sync()) {
+          if (LIS_ISSUE_PRED) {
             // plane pairs (A plane, B plane): hi*hi only, or hi*hi + hi*lo + lo*hi for split fp32
 #pragma unroll
             for (int pp = 0; pp < (P == 2 ? 3 : 1); ++pp) {

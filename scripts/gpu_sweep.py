@@ -80,3 +80,39 @@ if "c3" in which:
     lens = torch.randint(256, 769, (200_000,), generator=torch.Generator().manual_seed(3003)).tolist()
     report("c3_slice_1q32_vs_200k_ragged256-768", 1, 32, 200_000, 0, [(0, 0), (256, 1, 1, 1)], ragged=lens)
     report("c3_slice_32q32_vs_200k_ragged256-768", 32, 32, 200_000, 0, [(0, 0), (256, 3, 2, 1)], ragged=lens)
+
+if "k3" in which:
+    import math
+    head = importlib.import_module("multi-modal_colpali_b200.head")
+    for n_tok, hidden in [(4 * 1030, 2048), (64 * 1030, 2048), (64 * 1030, 768), (256 * 1030, 1536)]:
+        g = torch.Generator().manual_seed(5)
+        h = torch.randn(n_tok, hidden, generator=g).to(torch.bfloat16).to(dev)
+        w = (torch.randn(128, hidden, generator=g) / math.sqrt(hidden)).to(torch.bfloat16).to(dev)
+        b = (0.1 * torch.randn(128, generator=g)).to(torch.bfloat16).to(dev)
+        m = torch.ones(n_tok, dtype=torch.int64, device=dev)
+        for _ in range(3):
+            head.project_normalize(h, w, b, m)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); head.project_normalize(h, w, b, m); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        # torch's own route for the same op (cuBLAS GEMM + 3 elementwise kernels), as the existing-Blackwell baseline
+        def ref():
+            x = torch.nn.functional.linear(h, w, b)
+            x = x / x.norm(dim=-1, keepdim=True)
+            return x * m.unsqueeze(-1)
+        for _ in range(3):
+            ref()
+        torch.cuda.synchronize()
+        tr = []
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ref(); e1.record(); torch.cuda.synchronize()
+            tr.append(e0.elapsed_time(e1))
+        byts = n_tok * hidden * 2.0 + n_tok * 256.0
+        rec = {"case": "k3_project_normalize", "n_tok": n_tok, "hidden": hidden, "ms_best": min(ts), "ms_torch_best": min(tr),
+               "gbs": byts / (min(ts) * 1e-3) / 1e9, "tflops": 2.0 * n_tok * hidden * 128 / (min(ts) * 1e-3) / 1e12}
+        print(json.dumps(rec), flush=True)
+        out.write(json.dumps(rec) + "\n"); out.flush()

@@ -443,3 +443,45 @@ def test_ingestion_dropins(lis, oracle, tmp_path):
     assert {p.payload["document_link"] for p in out.points} == {"doi:a", "doi:b"}
     best = out.points[0]
     assert best.payload["page_no"] == int(torch.argmax(want).item()) + 1
+
+
+# ---------------------------------------------------------------------------------------------
+def test_randomized_shapes_against_oracle(lis, oracle):
+    """Seeded sweep over ragged shapes, including 0/1-token pages, many tiny pages per tile, queries
+    longer than an M tile and page counts around the CTA count (148) and the 128-page block size."""
+    g = torch.Generator().manual_seed(2026)
+    for trial in range(12):
+        nq = int(torch.randint(1, 9, (1,), generator=g))
+        q_lens = [int(x) for x in torch.randint(1, 70, (nq,), generator=g)]
+        if trial % 4 == 0:
+            q_lens[0] = int(torch.randint(129, 400, (1,), generator=g))
+        npg = [1, 2, 127, 128, 129, 147, 148, 149, 300, 1000, 2500, 37][trial]
+        hi = [40, 3, 300, 1100, 16][trial % 5]
+        p_lens = [int(x) for x in torch.randint(0 if trial % 3 == 0 else 1, hi + 1, (npg,), generator=g)]
+        if sum(p_lens) == 0:
+            p_lens[0] = 5
+        qs, ps = ragged(g, q_lens), ragged(g, p_lens)
+        bs = [128, 128, 32, 5][trial % 4]
+        blocks_ok = all(max(p_lens[j:j + bs]) > 0 for j in range(0, npg, bs))
+        if not blocks_ok:          # the reference cannot take the max over a block of empty pages
+            continue
+        want = oracle.score_multi_vector_widened(qs, ps, batch_size=bs)
+        got = lis.score_multi_vector(qs, ps, batch_size=bs, round_mode="f32")
+        assert got.shape == want.shape
+        assert (got - want).abs().max().item() <= TOL_F32, (trial, nq, npg, hi, bs)
+
+
+def test_many_queries_small_corpus(lis, oracle):
+    """256 queries x 32 tokens = 64 M tiles -> 22 passes over the store (multi-pass bookkeeping)."""
+    g = torch.Generator().manual_seed(17)
+    q = rand_unit(g, 256, 32, 128)
+    p = rand_unit(g, 150, 200, 128)
+    want = oracle.score_multi_vector_widened(q, p)
+    got = lis.score_multi_vector(q, p, round_mode="f32")
+    assert (got - want).abs().max().item() <= TOL_F32
+    idx = lis.LateInteractionIndex(150 * 200, 150)
+    idx.add(p)
+    wv, wi = oracle.topk(got, 20)
+    v, i = idx.search(q, 20)
+    assert torch.equal(i, wi) and torch.equal(v, wv)
+    idx.close()
