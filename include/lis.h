@@ -162,11 +162,13 @@ int lis_merge_topk(const float* cand_scores, const int64_t* cand_ids, int64_t nq
  * K3: retrieval head.  out[t,:] = mask[t] * normalize(W h[t,:] + b)   (no epsilon, like the
  * reference), written as 16-bit rows ready for the page store.
  *   hidden  device [n_tok, hidden_dim] dtype;  weight device [128, hidden_dim] dtype (row-major,
- *   i.e. torch Linear.weight);  bias device [128] dtype or NULL;  mask device uint8/ int64-free
- *   [n_tok] uint8 or NULL;  out device [n_tok,128] dtype.  hidden_dim % 64 == 0.
+ *   i.e. torch Linear.weight);  bias device [128] dtype or NULL;  mask device [n_tok] integers of
+ *   mask_itemsize bytes (1, 4 or 8: bool/uint8, int32, int64 attention masks are taken as they are)
+ *   or NULL;  out device [n_tok,128] dtype.  hidden_dim % 64 == 0.
  */
 int lis_project_normalize(const void* hidden, int64_t n_tok, int64_t hidden_dim, const void* weight,
-                          const void* bias, const uint8_t* mask, int dtype, void* out, void* stream);
+                          const void* bias, const void* mask, int mask_itemsize, int dtype, void* out,
+                          void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Page index: the GPU-resident replacement for the Qdrant multivector collection.

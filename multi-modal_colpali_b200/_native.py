@@ -51,7 +51,7 @@ SIGNATURES = {
     "lis_topk_workspace_bytes": (_i64, [_i64, _i64, _i32]),
     "lis_topk": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp]),
     "lis_merge_topk": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp]),
-    "lis_project_normalize": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "lis_project_normalize": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "lis_index_create": (_i32, [C.POINTER(_vp), _i32, _i32, _i64, _i64]),
     "lis_index_destroy": (None, [_vp]),
     "lis_index_add": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),

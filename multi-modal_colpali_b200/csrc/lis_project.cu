@@ -20,7 +20,8 @@ constexpr int kPThreads = 192;
 
 struct ProjectArgs {
   const void* bias;     // [128] 16-bit or null
-  const uint8_t* mask;  // [n_tok] or null
+  const void* mask;     // [n_tok] integers of mask_size bytes (1, 4 or 8), or null
+  int32_t mask_size;
   void* out;            // [n_tok, 128] 16-bit
   int64_t n_tok;
   int32_t kblocks;      // hidden_dim / 64
@@ -133,7 +134,14 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
         }
       }
       const float nrm = sqrtf(ss);
-      const float m = (args.mask == nullptr || tok >= args.n_tok) ? 1.f : (__ldg(args.mask + tok) ? 1.f : 0.f);
+      float m = 1.f;
+      if (args.mask != nullptr && tok < args.n_tok) {
+        bool on;
+        if (args.mask_size == 1) on = __ldg(static_cast<const uint8_t*>(args.mask) + tok) != 0;
+        else if (args.mask_size == 4) on = __ldg(static_cast<const int32_t*>(args.mask) + tok) != 0;
+        else on = __ldg(static_cast<const long long*>(args.mask) + tok) != 0;
+        m = on ? 1.f : 0.f;
+      }
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
@@ -203,8 +211,10 @@ static int encode_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t c
 using namespace lis;
 
 extern "C" int lis_project_normalize(const void* hidden, int64_t n_tok, int64_t hidden_dim, const void* weight,
-                                     const void* bias, const uint8_t* mask, int dtype, void* out,
+                                     const void* bias, const void* mask, int mask_itemsize, int dtype, void* out,
                                      void* stream) {
+  LIS_REQUIRE(mask == nullptr || mask_itemsize == 1 || mask_itemsize == 4 || mask_itemsize == 8,
+              "mask_itemsize must be 1, 4 or 8");
   LIS_REQUIRE(hidden && weight && out, "lis_project_normalize: null pointer");
   LIS_REQUIRE(dtype == LIS_BF16 || dtype == LIS_F16, "dtype must be bf16 or f16");
   LIS_REQUIRE(n_tok > 0 && n_tok < (int64_t(1) << 31), "n_tok=%lld out of range", (long long)n_tok);
@@ -228,7 +238,7 @@ extern "C" int lis_project_normalize(const void* hidden, int64_t n_tok, int64_t 
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   ProjectArgs a;
-  a.bias = bias; a.mask = mask; a.out = out; a.n_tok = n_tok;
+  a.bias = bias; a.mask = mask; a.mask_size = mask_itemsize; a.out = out; a.n_tok = n_tok;
   a.kblocks = (int32_t)(hidden_dim / 64);
   a.is_bf16 = dtype == LIS_BF16;
   const int64_t ntiles = (n_tok + kPTile - 1) / kPTile;

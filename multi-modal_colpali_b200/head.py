@@ -37,10 +37,15 @@ def project_normalize(hidden: torch.Tensor, weight: torch.Tensor, bias: Optional
     if attention_mask is not None:
         if attention_mask.shape != lead:
             raise ValueError("attention_mask must match hidden's leading dimensions")
-        m = (attention_mask.reshape(-1) != 0).to(device=dev, dtype=torch.uint8).contiguous()
+        m = attention_mask.reshape(-1).to(dev).contiguous()
+        if m.dtype == torch.bool:
+            m = m.view(torch.uint8)
+        if m.element_size() not in (1, 4, 8) or m.is_floating_point():
+            m = (m != 0).view(torch.uint8)
     out = torch.empty((h2.shape[0], N.DIM), dtype=dt, device=dev)
     with torch.cuda.device(dev):
         N.check(lib.lis_project_normalize(h2.data_ptr(), h2.shape[0], hdim, w.data_ptr(),
                                           None if b is None else b.data_ptr(), None if m is None else m.data_ptr(),
-                                          _DTYPES[dt], out.data_ptr(), _stream(dev)))
+                                          0 if m is None else m.element_size(), _DTYPES[dt], out.data_ptr(),
+                                          _stream(dev)))
     return out.reshape(*lead, N.DIM)
