@@ -108,11 +108,21 @@ class ClockSampler:
 # reference arm / CPU baseline: the oracle (a port of colpali-engine's score_multi_vector; the
 # package itself is not installable here -- DESIGN.md) on the host cores, bounded sample.
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps: int, warmup: int, sample_pages: int, dtype=torch.bfloat16):
+def cpu_reference_run(steps: int, warmup: int, sample_pages, dtype=torch.bfloat16, budget_s: float = 20.0):
+    """Time the restated score_multi_vector on the host cores.  ``sample_pages`` None -> sized from a probe call
+    so that the whole run (warm-up + timed calls) is about ``budget_s`` seconds of CPU work on this box."""
     from oracle import maxsim_oracle as oracle  # the only place bench.py executes oracle/
 
     q = make_queries().to(dtype)
     g = torch.Generator().manual_seed(2002)
+    if sample_pages is None:
+        probe = unit_rows(torch.randn(64, PAGE_TOK, DIM, generator=g)).to(dtype)
+        oracle.score_multi_vector(q, probe, device="cpu")
+        t0 = time.perf_counter()
+        oracle.score_multi_vector(q, probe, device="cpu")
+        per_page = (time.perf_counter() - t0) / 64
+        sample_pages = int(budget_s / max(steps + warmup, 1) / max(per_page, 1e-9))
+        sample_pages = max(128, min(sample_pages, 8192)) // 128 * 128     # whole 128-page blocks, <= 2.2 GB of bf16
     p = unit_rows(torch.randn(sample_pages, PAGE_TOK, DIM, generator=g)).to(dtype)
     for _ in range(warmup):
         oracle.score_multi_vector(q, p, device="cpu")
@@ -126,8 +136,9 @@ def cpu_reference_run(steps: int, warmup: int, sample_pages: int, dtype=torch.bf
     return {
         "value": pairs * steps / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
         "sample": f"{NQ} queries x {QTOK} tokens vs {sample_pages} pages x {PAGE_TOK} tokens, {str(dtype).split('.')[-1]}, "
-                  f"{steps} timed calls of the restated score_multi_vector on CPU torch ({os.cpu_count()} logical cpus)",
-        "ms_per_step": 1e3 * total / steps,
+                  f"{steps} timed calls ({total:.1f} s) of the restated score_multi_vector on CPU torch "
+                  f"({torch.get_num_threads()} threads, {os.cpu_count()} logical cpus)",
+        "ms_per_step": 1e3 * total / steps, "sample_pages": sample_pages,
     }
 
 
@@ -135,12 +146,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = cpu_reference_run(args.steps, args.warmup, args.ref_pages)
+    res = cpu_reference_run(args.steps, args.warmup, args.ref_pages, budget_s=120.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(args, args.ref_pages, note="bounded sample of the same workload on host cores"),
+        "config": workload_config(args, res["sample_pages"], note="bounded sample of the same workload on host cores"),
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -284,7 +295,7 @@ def run_ours(args):
     }
 
     if rank == 0:
-        cpu = cpu_reference_run(3, 1, args.ref_pages) if world == 1 and not args.no_cpu else None
+        cpu = cpu_reference_run(3, 1, args.ref_pages, budget_s=20.0) if world == 1 and not args.no_cpu else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -314,7 +325,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--pages", type=int, default=DEFAULT_PAGES, help="pages per GPU")
-    ap.add_argument("--ref-pages", type=int, default=256, help="pages in the bounded CPU sample")
+    ap.add_argument("--ref-pages", type=int, default=None,
+                    help="pages in the bounded CPU sample (default: sized from a probe call, ~20 s / ~2 min of CPU work)")
     ap.add_argument("--search-iters", type=int, default=50)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--traffic", type=float, default=None,

@@ -11,6 +11,7 @@ from .reference_api import (MaxSimClient, PointStruct, QueryResponse, ScoredPoin
                             retrieve_colpali, score_results, index_for_dataset, load_embedding_cache,
                             create_document_embeddings, colpali_qdrant)
 from .sharded import ShardedIndex, shard_range, balanced_shard_ranges, gather_candidates
+from .batching import QueryBatcher
 
 __all__ = [
     "score_multi_vector", "plan_queries", "clamp_flags", "maxsim_scores_device", "pack_queries", "build_page_store",
@@ -18,5 +19,5 @@ __all__ = [
     "MaxSimClient", "PointStruct", "QueryResponse", "ScoredPoint", "ensure_colpali_collection",
     "retrieve_colpali", "score_results", "index_for_dataset", "load_embedding_cache",
     "create_document_embeddings", "colpali_qdrant",
-    "ShardedIndex", "shard_range", "balanced_shard_ranges", "gather_candidates",
+    "ShardedIndex", "shard_range", "balanced_shard_ranges", "gather_candidates", "QueryBatcher",
 ]

@@ -92,3 +92,42 @@ def test_embedding_cache_loader_validates(lis, tmp_path):
         pickle.dump({"not": "a list"}, f)
     with pytest.raises(ValueError):
         lis.load_embedding_cache(str(tmp_path / "bad.pkl"))
+
+
+def test_query_batcher_coalesces_and_routes_results(lis):
+    """Host logic only: a fake index records the batches it is given."""
+    import threading
+
+    calls = []
+
+    class FakeIndex:
+        def search(self, qs, k, round_mode):
+            calls.append(len(qs))
+            s = torch.stack([torch.arange(k, 0, -1, dtype=torch.float32) + float(q[0, 0]) for q in qs])
+            i = torch.stack([torch.arange(k, dtype=torch.int64) + int(q[0, 0]) * 100 for q in qs])
+            return s, i
+
+    b = lis.QueryBatcher(FakeIndex(), max_rows=64, max_wait_ms=50)
+    outs = {}
+
+    def client(j):
+        q = torch.full((16, 128), float(j))
+        outs[j] = b.search(q, 3 + (j % 2))
+
+    ts = [threading.Thread(target=client, args=(j,)) for j in range(8)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    b.close()
+    assert b.served == 8 and sum(calls) == 8 and max(calls) <= 4      # 64 rows = 4 queries of 16 tokens per pass
+    assert len(calls) < 8                                              # something was coalesced
+    for j in range(8):
+        s, i = outs[j]
+        assert len(s) == 3 + (j % 2) and i[0].item() == j * 100 and s[0].item() - j in (3.0, 4.0)   # kmax of its batch
+
+    class Broken:
+        def search(self, qs, k, round_mode):
+            raise RuntimeError("boom")
+
+    b = lis.QueryBatcher(Broken())
+    with pytest.raises(RuntimeError, match="boom"):
+        b.search(torch.zeros(4, 128), 2)
+    b.close()
