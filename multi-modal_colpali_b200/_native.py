@@ -47,6 +47,7 @@ SIGNATURES = {
     "lis_set_tuning": (_i32, [_i32, _i32, _i32, _i32, _i32]),
     "lis_launch_count": (_i64, []),
     "lis_set_ablation": (_i32, [_i32]),
+    "lis_k1_stats": (_i32, [_vp]),
     "lis_debug_sim_tile": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "lis_topk_workspace_bytes": (_i64, [_i64, _i64, _i32]),
     "lis_topk": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp]),

@@ -86,7 +86,6 @@ __global__ void merge_planes_kernel(const __nv_bfloat16* __restrict__ hi, const 
     out[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
 }
 
-static inline int planes_of(const lis_index* ix) { return ix->dtype == LIS_F32X2 ? 2 : 1; }
 static inline int elem_dtype(const lis_index* ix) { return ix->dtype == LIS_F32X2 ? LIS_BF16 : ix->dtype; }
 static inline uint8_t* lo_plane(const lis_index* ix) {
   return static_cast<uint8_t*>(ix->tokens) + (size_t)ix->cap_rows * 256;

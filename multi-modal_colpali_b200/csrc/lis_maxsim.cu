@@ -19,6 +19,7 @@ void set_error(const char* fmt, ...) {
 }
 std::atomic<int64_t> g_launches{0};
 Tuning g_tuning;
+static long long* g_stats = nullptr;
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -103,7 +104,7 @@ static int launch_maxsim(const Maps& m, const MaxSimArgs& a, int grid, cudaStrea
     LIS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  kern<<<grid, 64 + 128 * EH, smem, st>>>(m.q, m.p, m.q2, m.p2, a, ns);
+  kern<<<grid, kCtrlThreads + 128 * EH, smem, st>>>(m.q, m.p, m.q2, m.p2, a, ns);
   count_launch();
   LIS_CUDA_CHECK(cudaGetLastError());
   return LIS_OK;
@@ -153,8 +154,12 @@ extern "C" {
 const char* lis_last_error(void) { return g_err; }
 int lis_abi_version(void) { return LIS_ABI_VERSION; }
 int64_t lis_launch_count(void) { return g_launches.load(); }
+int lis_k1_stats(long long* device_buf) {
+  g_stats = device_buf;  // 8 x int64 on the device, zeroed by the caller; null switches the counters off
+  return LIS_OK;
+}
 int lis_set_ablation(int mode) {
-  LIS_REQUIRE(mode >= 0 && mode <= 2, "ablation mode must be 0, 1 or 2");
+  LIS_REQUIRE(mode >= 0 && mode <= 4, "ablation mode must be in 0..4");
   g_tuning.ablate = mode;
   return LIS_OK;
 }
@@ -368,6 +373,7 @@ static int maxsim_impl(const void* q, const void* q_lo, int64_t q_rows, const in
     a.round_mode = round_mode;
     a.is_bf16 = dtype == LIS_BF16;
     a.ablate = g_tuning.ablate;
+    a.stats = g_stats;
     // the instantiation whose group equals this pass's tile count (the last pass may be short)
     rc = dispatch_maxsim(nt, a.n_mt, atm, m, a, grid, st, false, planes);
     if (rc) return rc;
@@ -463,6 +469,7 @@ int lis_debug_sim_tile(const void* q, int64_t q_rows, const void* tokens, int64_
   a.out = dummy; a.dbg = out; a.ld_out = 1; a.np = 1; a.mt0 = 0; a.n_mt = 1; a.round_mode = 0;
   a.is_bf16 = dtype == LIS_BF16;
   a.ablate = 0;
+  a.stats = nullptr;
   a.q = q;
   a.q_rows = q_rows;
   rc = dispatch_maxsim(tile_n, 1, a_in_tmem != 0, m, a, 1, st, true);

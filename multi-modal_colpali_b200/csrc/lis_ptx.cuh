@@ -34,10 +34,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// try_wait suspends the thread in hardware until the phase completes or a time limit passes; the
-// hint (ns) keeps a waiting warp off the issue ports instead of spinning.
+// try_wait suspends the thread in hardware until the phase completes or a time limit passes.
+// LIS_WAIT_MODE (experiments): 0 = try_wait with a suspend-time hint, 1 = plain try_wait, 2 = test_wait (pure polling).
+#ifndef LIS_WAIT_MODE
+#define LIS_WAIT_MODE 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if LIS_WAIT_MODE == 0
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -45,6 +49,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
       : "memory");
+#elif LIS_WAIT_MODE == 1
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+#endif
   return ok != 0;
 }
 // Bounded wait: a pipeline bug must surface as a launch failure, never as a hung GPU.

@@ -30,9 +30,31 @@ def run(n=20):
 
 
 run(40)  # reach the power-capped steady state
-for rnd in range(3):
-    for mode, name in [(0, "full"), (2, "no max"), (1, "no tmem loads, no max")]:
+for rnd in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
+    for mode, name in [(0, "full"), (2, "no max"), (1, "no tmem loads, no max"), (3, "no TMA traffic"),
+                       (4, "no TMA traffic, no tmem loads, no max")]:
         native.check(lib.lis_set_ablation(mode))
         ms = run()
         print(json.dumps({"round": rnd, "mode": name, "ms": ms, "tflops": flops / ms / 1e9}), flush=True)
+lib.lis_set_ablation(0)
+# cycle attribution inside CTA 0 (one launch per mode); needs the LIS_K1_STATS build (LIS_LIB=.../liblis_stats.so)
+import os
+if "stats" not in os.environ.get("LIS_LIB", ""):
+    sys.exit(0)
+stats = torch.zeros(32, dtype=torch.int64, device=dev)
+for mode, name in [(0, "full"), (1, "no tmem loads, no max"), (3, "no TMA traffic"), (4, "no TMA traffic, no tmem loads, no max")]:
+    native.check(lib.lis_set_ablation(mode))
+    run(5)
+    stats.zero_()
+    native.check(lib.lis_k1_stats(stats.data_ptr()))
+    scoring.maxsim_scores_device(pq, store, "f32", out=scores)
+    torch.cuda.synchronize()
+    native.check(lib.lis_k1_stats(None))
+    s = stats.tolist()
+    uses = max(s[3], 1)
+    print(json.dumps({"mode": name, "mma_loop_cycles_per_use": s[0] / uses, "mma_wait_tiles_per_use": s[1] / uses,
+                      "mma_wait_acc_per_use": s[2] / uses, "mma_issue_per_use": s[23] / uses,
+                      "epi_wait_full_per_use_by_warp": [round(s[4 + 2 * w] / uses) for w in range(8)],
+                      "epi_hold_per_use_by_warp": [round(s[5 + 2 * w] / uses) for w in range(8)], "uses": s[3],
+                      "w0_finish_cycles_each": s[20] / max(s[21], 1), "w0_finishes": s[21], "w0_post_release_per_use": s[22] / uses}), flush=True)
 lib.lis_set_ablation(0)

@@ -29,12 +29,14 @@ __global__ void __launch_bounds__(128, 1) mma_rate(int groups, long long* cycles
     const uint32_t a_base = smem_u32(smem);
     const uint32_t b_base = a_base + 96 * 1024;
     const long long t0 = clock64();
+    long long issue_cycles = 0;
     for (int g = 0; g < groups; ++g) {
       const uint32_t a = a_base + (g % 3) * 32768;
       const uint32_t b = b_base + ((g / 3) & 1) * (N * 256);
       const uint32_t d = tmem + (TS ? 192 : 0) + (g & 1) * N;
       if (g >= 2) mbar_wait(bars + (g & 1), ((g - 2) >> 1) & 1);
       if (ELECT) { if (!elect_one_sync()) continue; }
+      const long long i0 = clock64();
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const uint32_t ka = (k >> 2) * 16384 + (k & 3) * 32;
@@ -43,10 +45,11 @@ __global__ void __launch_bounds__(128, 1) mma_rate(int groups, long long* cycles
         else umma_f16(d, make_kmajor_sw128_desc(a + ka), make_kmajor_sw128_desc(b + kb), idesc, k > 0);
       }
       umma_commit(bars + (g & 1));
+      issue_cycles += clock64() - i0;
     }
     mbar_wait(bars + ((groups - 1) & 1), ((groups - 1) >> 1) & 1);
     const long long t1 = clock64();
-    if ((threadIdx.x & 31) == 0) cycles[blockIdx.x] = t1 - t0;
+    if (ELECT ? elect_one_sync() : true) { cycles[blockIdx.x] = t1 - t0; cycles[148 + blockIdx.x] = issue_cycles; }
   }
   tc_fence_before();
   __syncthreads();
@@ -56,7 +59,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate(int groups, long long* cycles
 template <int N, bool TS, bool ELECT>
 void run() {
   long long* d;
-  cudaMalloc(&d, 148 * 8);
+  cudaMalloc(&d, 2 * 148 * 8);
   const int smem = (96 + 128) * 1024;
   cudaFuncSetAttribute(mma_rate<N, TS, ELECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int groups = 20000;
@@ -69,18 +72,19 @@ void run() {
   cudaEventRecord(e1);
   cudaError_t e = cudaDeviceSynchronize();
   float ms; cudaEventElapsedTime(&ms, e0, e1);
-  long long h[148];
+  long long h[296];
   cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  double iss = 0; for (int i = 0; i < 148; ++i) iss += h[148 + i]; iss /= 148;
   double avg = 0; for (int i = 0; i < 148; ++i) avg += h[i]; avg /= 148;
   const double per_mma = avg / (groups * 8.0);
   const double flops = 148.0 * groups * 8 * 2.0 * 128 * N * 16;
   printf("%s N=%3d cycles/MMA=%6.1f (ideal %d)  util=%.3f  wall %.3f ms -> %.1f TFLOP/s, eff clock %.0f MHz  (%s)\n", ELECT ? (TS ? "TS/elect" : "SS/elect") : (TS ? "TS/lane0" : "SS/lane0"), N, per_mma, N / 2,
          (N / 2) / per_mma, ms, flops / (ms * 1e-3) / 1e12, avg / (ms * 1e-3) / 1e6, cudaGetErrorString(e));
+  printf("      issue (8 MMAs + commit) takes %.0f cycles of the %.0f-cycle group period\n", iss / groups, avg / groups);
   cudaFree(d);
 }
 
 int main() {
-  run<256, false, false>(); run<128, false, false>(); run<64, true, false>();
-  run<256, false, true>(); run<128, false, true>(); run<128, true, true>(); run<64, true, true>(); run<32, true, true>();
+  run<256, false, true>(); run<128, false, true>(); run<64, true, true>();
   return 0;
 }
