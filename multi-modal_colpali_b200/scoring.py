@@ -293,7 +293,7 @@ def maxsim_scores_device(pq: PackedQueries, store: PageStore, round_mode: str = 
 
 def score_multi_vector(qs: TensorOrList, ps: TensorOrList, batch_size: int = 128,
                        device: Union[str, torch.device, None] = None, *, round_mode: str = "reference",
-                       return_device: bool = False) -> torch.Tensor:
+                       return_device: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``score[b, c] = sum_n max_s <qs[b][n], ps[c][s]>`` -- same signature, zero-padding semantics,
     error behaviour and CPU-float32 ``[len(qs), len(ps)]`` result as colpali-engine's
     ``score_multi_vector`` (05_experiment02.py:214).
@@ -305,12 +305,17 @@ def score_multi_vector(qs: TensorOrList, ps: TensorOrList, batch_size: int = 128
     (error ~1e-6 on unit-norm rows, inside the 1e-4 bar); ``round_mode`` does not apply to them.  ``batch_size`` only matters through the
     padding it implies in the reference: a page shorter than the longest page of its block has its
     per-token max clamped at 0.  Inputs may live on any device; the corpus is not copied when it is
-    already a contiguous CUDA tensor.
+    already a contiguous CUDA tensor.  ``out``: optional CPU float32 ``[len(qs), len(ps)]`` tensor to
+    receive the scores (pin it to make the device-to-host copy DMA-direct).
     """
     if len(qs) == 0:
         raise ValueError("No queries provided")
     if len(ps) == 0:
         raise ValueError("No passages provided")
+    q_dt = qs.dtype if isinstance(qs, torch.Tensor) else qs[0].dtype
+    p_dt = ps.dtype if isinstance(ps, torch.Tensor) else ps[0].dtype
+    if q_dt != p_dt:   # torch.einsum in the reference refuses mixed dtypes too (HF port: processing_colpali.py:342)
+        raise ValueError(f"Queries and passages must have the same dtype (queries are {q_dt}, passages {p_dt})")
     dev = resolve_device(device)
     N.check(N.load().lis_device_supported(dev.index))
     with torch.cuda.device(dev):
@@ -321,4 +326,10 @@ def score_multi_vector(qs: TensorOrList, ps: TensorOrList, batch_size: int = 128
         scores = maxsim_scores_device(pq, store, round_mode)
         if return_device:
             return scores
+        if out is not None:
+            if out.device.type != "cpu" or out.dtype != torch.float32 or tuple(out.shape) != tuple(scores.shape):
+                raise ValueError(f"out must be a CPU float32 tensor of shape {tuple(scores.shape)}")
+            out.copy_(scores, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            return out
         return scores.cpu()

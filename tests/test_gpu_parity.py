@@ -485,3 +485,39 @@ def test_many_queries_small_corpus(lis, oracle):
     v, i = idx.search(q, 20)
     assert torch.equal(i, wi) and torch.equal(v, wv)
     idx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+def test_error_paths_and_limits(lis, oracle):
+    """Capacity / argument errors surface as Python exceptions with the C-side message; big k; out= buffer."""
+    g = torch.Generator().manual_seed(18)
+    idx = lis.LateInteractionIndex(100, 3)
+    with pytest.raises(ValueError, match="row capacity"):
+        idx.add([rand_unit(g, 101, 128)])
+    idx.add([rand_unit(g, 30, 128), rand_unit(g, 30, 128), rand_unit(g, 30, 128)])
+    with pytest.raises(ValueError, match="page capacity"):
+        idx.add([rand_unit(g, 1, 128)])
+    with pytest.raises(ValueError, match="k out of range|k=|out of range"):
+        idx.search(rand_unit(g, 1, 8, 128), 5000)
+    with pytest.raises(ValueError):
+        idx.search(torch.zeros(1, 8, 64, dtype=torch.bfloat16), 2)       # wrong embedding width
+    v, i = idx.search(rand_unit(g, 2, 8, 128), 8)                          # k > number of pages
+    assert (i[:, 3:] == -1).all() and torch.isinf(v[:, 3:]).all() and sorted(i[0, :3].tolist()) == [0, 1, 2]
+    idx.close()
+    with pytest.raises(ValueError, match="mix dtypes"):
+        lis.score_multi_vector([rand_unit(g, 4, 128), rand_unit(g, 4, 128).float()], [rand_unit(g, 4, 128)])
+    with pytest.raises(ValueError, match="queries are"):
+        lis.score_multi_vector(rand_unit(g, 1, 4, 128), rand_unit(g, 2, 4, 128).to(torch.float16))
+    # k = 1024 (LIS_MAX_K) over a multi-pass row, and the out= host buffer
+    q = rand_unit(g, 3, 10, 128)
+    p = rand_unit(g, 9000, 12, 128)
+    out = torch.empty(3, 9000, dtype=torch.float32).pin_memory()
+    got = lis.score_multi_vector(q, p, round_mode="f32", out=out)
+    assert got is out
+    want = oracle.score_multi_vector_widened(q, p)
+    assert (out - want).abs().max().item() <= TOL_F32
+    wv, wi = oracle.topk(out, 1024)
+    gv, gi = lis.topk_device(out.cuda(), 1024)
+    assert torch.equal(gi.cpu(), wi) and torch.equal(gv.cpu(), wv)
+    with pytest.raises(ValueError, match="out must be"):
+        lis.score_multi_vector(q, p, out=torch.empty(3, 5))
