@@ -129,7 +129,7 @@ int lis_set_tuning(int tile_n, int group, int max_ctas, int epi_halves, int a_op
  * the max arithmetic, 3 = the producer issues no TMA loads after the first ring fill (stale tiles are reused),
  * 4 = 3 and 1 together; 0 restores normal operation.  Used by scripts/gpu_ablate.py to attribute time. */
 int lis_set_ablation(int mode);
-/* Timing experiments: point K1 at 32 zeroed int64 on the device; CTA 0 then accumulates cycle counters there
+/* Timing experiments: point K1 at 256 zeroed int64 on the device; CTA 0 then accumulates cycle counters there
  * ([0] MMA-warp loop, [1] its waits for page tiles, [2] its waits for a free accumulator, [3] uses,
  * [4+2w] epilogue warp w waiting for a full accumulator, [5+2w] holding it).  NULL switches them off. */
 int lis_k1_stats(long long* device_buf);

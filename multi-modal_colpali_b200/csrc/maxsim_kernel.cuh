@@ -32,6 +32,10 @@
 #ifndef LIS_MMA_WARPS
 #define LIS_MMA_WARPS 2
 #endif
+// Accumulator chunks (32 columns) an epilogue warp holds in registers at once.
+#ifndef LIS_EPI_GRP
+#define LIS_EPI_GRP 4
+#endif
 #ifdef LIS_MMA_ISSUE_LANE0
 #define LIS_ISSUE_PRED (lane == 0)
 #else
@@ -166,11 +170,11 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
   int64_t* range = reinterpret_cast<int64_t*>(tmem_slot + 2);  // [0]=page begin [1]=page end [2]=row0
   float* srm = reinterpret_cast<float*>(range + 4);            // [2][EH*128] row-max exchange
-  constexpr int kPW = 48;                                      // page-table window (pages)
+  constexpr int kPW = 96;                                      // page-table window (pages)
   uint64_t* ex_full = reinterpret_cast<uint64_t*>(srm + 2 * EH * kMTile);  // [2] exchange slot published by all epilogue warps
   uint64_t* ex_empty = ex_full + 2;                                        // [2] ... consumed by the reducer warp
   int64_t* ex_meta = reinterpret_cast<int64_t*>(ex_empty + 2);             // [2][2] page index, (g | clamp << 8)
-  int64_t* pw_end = ex_meta + 4;                                           // [kPW] end row of page w0+i
+  int32_t* pw_end = reinterpret_cast<int32_t*>(ex_meta + 4);              // [kPW] end row (relative to row0) of page w0+i
   uint8_t* pw_clamp = reinterpret_cast<uint8_t*>(pw_end + kPW);          // [kPW] clamp flag of page w0+i
   uint16_t* segtab = reinterpret_cast<uint16_t*>(pw_clamp + kPW);        // [G][16] lo | hi<<8 of the tile's first segments
   int32_t* seginfo = reinterpret_cast<int32_t*>(segtab + G * 16);        // [G][2] first segment, segment count
@@ -289,7 +293,10 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           issued = true;
           const uint32_t a = use % NACC;
           c0 = st_on ? clock64() : 0;
+          const bool tl = LIS_STATS_ON(args) && blockIdx.x == 0 && use >= 1000 && use < 1008 && lane == 0;
+          if (tl) args.stats[32 + (use - 1000) * 5 + 0] = clock64();      // MMA warp reaches the acc_empty wait
           mbar_wait(acc_empty + a, ((use / NACC) & 1u) ^ 1u);
+          if (tl) args.stats[32 + (use - 1000) * 5 + 1] = clock64();      // ... passes it
           if (st_on) st_acc += clock64() - c0;
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + kACols + a * NT;
@@ -318,6 +325,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             umma_commit(acc_full + a);
           }
           __syncwarp();
+          if (tl) args.stats[32 + (use - 1000) * 5 + 2] = clock64();      // ... has issued the MMAs + commit
           if (st_on) st_issue += clock64() - ic0;
         }
         // hand the page tile back: after this warp's MMAs on it have completed (or at once if it had none)
@@ -433,24 +441,25 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       rm[G - 1] = cur;
     };
 
-    // Emit one finished page for M tile g: every epilogue thread publishes its partial row max; after
-    // the barrier each WARP takes whole segments (queries) of the tile: its lanes combine the two
-    // column halves (max), clamp / round like the reference, and the segment's rows are added up by a
-    // fixed shuffle tree (deterministic).  Spreading the sums over all epilogue warps keeps any one of
-    // them from falling behind the accumulator ring -- a single summing thread per segment made its
-    // warp the straggler the MMA warp waited for (profiles/README_r1.md, cycle counters).
-    // page-table window [w0, w0+kPW): end rows and clamp flags of the pages around the cursor.  Every
+    // All page bookkeeping below is 32-bit and relative to this CTA's range: page index pi = p - pa,
+    // rows relative to row0 (a CTA's range is < 2^31 rows).  Barrier addresses are taken once.
+    const uint32_t acc_full_u = smem_u32(acc_full), acc_empty_u = smem_u32(acc_empty);
+    const uint32_t ex_full_u = smem_u32(ex_full), ex_empty_u = smem_u32(ex_empty);
+    const int npages = (int)(pb - pa);
+
+    // page-table window [w0, w0+kPW): relative end rows and clamp flags of the pages around the
+    // cursor, in shared memory (L1 is ~4 KB here; a global read would be an L2 round trip).  Every
     // epilogue thread walks the pages in the same order, so refills are collective (two barriers).
-    int64_t w0 = 0;
-    auto refill = [&](int64_t base) {
+    int w0 = 0;
+    auto refill = [&](int base) {
       named_bar_sync(1, 128 * EH);            // nobody still reads the old window
       if (etid < kPW) {
-        const int64_t pg = base + etid;
-        int64_t e = 0;
+        const int pg = base + etid;
+        int e = 0;
         uint8_t c = 0;
-        if (pg < pb) {
-          e = __ldg(args.p_offsets + pg + 1);
-          if (args.p_clamp != nullptr) c = __ldg(args.p_clamp + pg);
+        if (pg < npages) {
+          e = (int)(__ldg(args.p_offsets + pa + pg + 1) - row0);
+          if (args.p_clamp != nullptr) c = __ldg(args.p_clamp + pa + pg);
         }
         pw_end[etid] = e;
         pw_clamp[etid] = c;
@@ -468,59 +477,59 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                                         ((__ldg(args.seg_hi + first + j) - mt * kMTile) << 8));
     }
 
-    long long st_fin = 0, st_nfin = 0, st_post = 0;
     // Publish one finished page of M tile g: the partial row maxima of this thread go into the next
     // exchange slot and the warp arrives on the slot's barrier -- nobody waits for anybody here;
     // the reducer warp takes over once all epilogue warps have arrived.
     uint32_t fin = 0;
-    auto finish_page = [&](int g, int64_t p, float v) {
-      const long long fc0 = LIS_STATS_ON(args) ? clock64() : 0;
+    auto finish_page = [&](int g, int pi, float v) {
       const uint32_t slot = fin & 1u;
-      mbar_wait(ex_empty + slot, ((fin >> 1) & 1u) ^ 1u);     // slot drained by the reducer (2 finishes ago)
+      mbar_wait_u32(ex_empty_u + slot * 8, ((fin >> 1) & 1u) ^ 1u);   // slot drained by the reducer (2 finishes ago)
       srm[slot * (EH * kMTile) + etid] = v;
       if (etid == 0) {
-        ex_meta[2 * slot] = p;
-        ex_meta[2 * slot + 1] = (int64_t)g | ((int64_t)pw_clamp[p - w0] << 8);
+        ex_meta[2 * slot] = pa + pi;
+        ex_meta[2 * slot + 1] = (int64_t)g | ((int64_t)pw_clamp[pi - w0] << 8);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(ex_full + slot);
+      if (lane == 0) mbar_arrive_u32(ex_full_u + slot * 8);
       ++fin;
-      if (LIS_STATS_ON(args)) { st_fin += clock64() - fc0; ++st_nfin; }
     };
 
     long long st_wait = 0, st_hold = 0;
     if (pa < pb) {
-      int64_t p = pa;                                   // current page
-      refill(pa);                                       // (also publishes the segment tables)
-      int64_t pend = pw_end[0];                         // its end row (global)
+      int p = 0;                                        // current page (relative)
+      refill(0);                                        // (also publishes the segment tables)
+      int pend = pw_end[0];                             // its end row (relative to row0)
       uint32_t use = 0;
-      constexpr int GRP = (NOWN % 4 == 0) ? 4 : (NOWN % 3 == 0 ? 3 : 2);  // chunks held in registers at once
+      // chunks held in registers at once: 4 (all of the warp's loads in flight before the release)
+      // measured 2-3 % faster than 2 on the 3-tile pass despite sitting at the 168-register cap
+      constexpr int GRP = (NOWN % LIS_EPI_GRP == 0) ? LIS_EPI_GRP : (NOWN % 3 == 0 ? 3 : 2);
       static_assert(NOWN % GRP == 0, "chunk grouping");
+      const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + kACols + c_lo * 32;
       for (int t = 0; t < ntiles; ++t) {
-        const int64_t trow = row0 + (int64_t)t * NT;    // global row of column 0
+        const int tcol = t * NT;                        // row (relative) of this tile's column 0
         // end column of a page relative to this tile (saturated; > NT: the page continues)
-        auto rel_end = [&](int64_t e) { const int64_t d = e - trow; return d > NT ? NT + 1 : (int)d; };
+        auto rel_end = [&](int e) { const int d = e - tcol; return d > NT ? NT + 1 : d; };
         const int pe_tile = rel_end(pend);
-        int64_t p_next = p, pend_next = pend;
+        int p_next = p, pend_next = pend;
 #pragma unroll 1
         for (int g = 0; g < G; ++g) {
           const uint32_t a = use % NACC;
           const bool st_on = LIS_STATS_ON(args) && blockIdx.x == 0;
           const long long ec0 = st_on ? clock64() : 0;
-          mbar_wait(acc_full + a, (use / NACC) & 1u);
+          mbar_wait_u32(acc_full_u + a * 8, (use / NACC) & 1u);
           const long long ec1 = st_on ? clock64() : 0;
           tc_fence_after();
           ++use;
-          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + kACols + a * NT + c_lo * 32;
-          int64_t pp = p, ppend = pend;     // rewind the page cursor for every M tile
-          bool live = pp < pb;
+          const uint32_t taddr = tlane + a * NT;
+          int pp = p, ppend = pend;         // rewind the page cursor for every M tile
+          bool live = pp < npages;
           int pe = pe_tile;
           float m = rm[0];
 
           auto next_page = [&]() {          // after a finish: advance the cursor
             m = -INFINITY;
             ++pp;
-            if (pp >= pb) { live = false; pe = NT + 1; return; }
+            if (pp >= npages) { live = false; pe = NT + 1; return; }
             if (pp >= w0 + kPW) refill(pp - p < kPW ? p : pp);
             ppend = pw_end[pp - w0];
             pe = rel_end(ppend);
@@ -562,9 +571,9 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             }
           };
 
-          // The accumulator buffer is the scarce resource (512/NT of them feed the tensor pipe):
-          // pull this warp's columns into registers with all loads in flight, hand the buffer
-          // straight back to the MMA warp, and only then do the arithmetic and the page logic.
+          // The accumulator buffer is the scarce resource (512/NT of them feed the tensor pipe): pull
+          // this warp's columns into registers, hand the buffer back to the MMA warps as soon as the
+          // last load has landed, and only then finish the arithmetic and the page logic.
 #pragma unroll
           for (int grp = 0; grp < NOWN / GRP; ++grp) {
             uint32_t v0[32], v1[32], v2[32], v3[32];
@@ -579,11 +588,10 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             if (grp == NOWN / GRP - 1) {
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(acc_empty + a);
+              if (lane == 0) mbar_arrive_u32(acc_empty_u + a * 8);
               if (st_on) {
                 st_wait += ec1 - ec0;          // epilogue warp: waiting for a full accumulator
                 st_hold += clock64() - ec1;    //                holding it (wake -> release)
-                st_post -= clock64();
               }
             }
             const int cb = (c_lo + grp * GRP) * 32;
@@ -605,7 +613,6 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             }
           }
           if (EH == 2 && half == 0) skip_to(NT);
-          if (st_on) st_post += clock64();     // release -> end of this use's arithmetic and page logic
           rotate(m);
           p_next = pp;
           pend_next = ppend;
@@ -615,10 +622,9 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       if (LIS_STATS_ON(args) && blockIdx.x == 0 && lane == 0) {
         args.stats[4 + 2 * warp] = st_wait;
         args.stats[5 + 2 * warp] = st_hold;
-        if (warp == 0) { args.stats[20] = st_fin; args.stats[21] = st_nfin; args.stats[22] = st_post; }
       }
       // pages not closed by any tile: trailing empty pages (or ntiles == 0)
-      while (p < pb) {
+      while (p < npages) {
         if (p < w0 || p >= w0 + kPW) refill(p);
 #pragma unroll 1
         for (int g = 0; g < G; ++g) {

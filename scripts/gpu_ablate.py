@@ -41,7 +41,7 @@ lib.lis_set_ablation(0)
 import os
 if "stats" not in os.environ.get("LIS_LIB", ""):
     sys.exit(0)
-stats = torch.zeros(32, dtype=torch.int64, device=dev)
+stats = torch.zeros(256, dtype=torch.int64, device=dev)
 for mode, name in [(0, "full"), (1, "no tmem loads, no max"), (3, "no TMA traffic"), (4, "no TMA traffic, no tmem loads, no max")]:
     native.check(lib.lis_set_ablation(mode))
     run(5)
@@ -52,6 +52,13 @@ for mode, name in [(0, "full"), (1, "no tmem loads, no max"), (3, "no TMA traffi
     native.check(lib.lis_k1_stats(None))
     s = stats.tolist()
     uses = max(s[3], 1)
+    t0 = min(x for x in s[32:72] if x > 0) if any(s[32:72]) else 0
+    tl = [[(s[32 + u * 5 + k] - t0) if s[32 + u * 5 + k] else None for k in range(5)] for u in range(8)]
+    print("timeline (cycles; per use: mma_wait_start, mma_wait_end, mma_issued, epi_wake, epi_release):", name)
+    for u, row in enumerate(tl):
+        wk = [s[96 + u * 16 + w] - t0 for w in range(8)]
+        rl = [s[96 + u * 16 + 8 + w] - t0 for w in range(8)]
+        print("   use", 1000 + u, row, "wake by warp", wk, "release by warp", rl)
     print(json.dumps({"mode": name, "mma_loop_cycles_per_use": s[0] / uses, "mma_wait_tiles_per_use": s[1] / uses,
                       "mma_wait_acc_per_use": s[2] / uses, "mma_issue_per_use": s[23] / uses,
                       "epi_wait_full_per_use_by_warp": [round(s[4 + 2 * w] / uses) for w in range(8)],
