@@ -98,6 +98,46 @@ class LateInteractionIndex:
                 self.payloads[i] = pay
         return id_arr
 
+    def add_padded(self, embeddings: torch.Tensor, attention_mask: torch.Tensor, ids: Optional[Sequence[int]] = None,
+                   payloads: Optional[Sequence[Any]] = None) -> np.ndarray:
+        """Append a padded encoder batch ``[B, S, 128]`` (what ``model(**batch)`` returns: rows where
+        ``attention_mask == 0`` are zero, on the left for ColQwen, on the right for ColPali) WITHOUT
+        storing the pad rows: they are dropped and the page is flagged for the reference's zero-padding
+        semantics instead (a zero row contributes similarity 0 to every max, i.e. ``max(v, 0)``), which is
+        bit-identical to scoring the padded tensor and costs none of its bandwidth."""
+        if embeddings.dim() != 3 or embeddings.shape[-1] != N.DIM or attention_mask.shape != embeddings.shape[:2]:
+            raise ValueError("expected embeddings [B, S, 128] and attention_mask [B, S]")
+        keep = attention_mask != 0
+        lens = keep.sum(dim=1).to(torch.int32).cpu().numpy()
+        rows = embeddings[keep.to(embeddings.device)]                 # ragged rows, page after page
+        n, s_pad = embeddings.shape[0], embeddings.shape[1]
+        first = len(self)
+        id_arr = np.arange(first, first + n, dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
+        if id_arr.shape != (n,):
+            raise ValueError("ids must have one entry per page")
+        clamp = (lens < s_pad).astype(np.uint8)
+        flat = rows.to(self.dtype).contiguous()
+        with torch.cuda.device(self.device):
+            N.check(self._lib.lis_index_add(self._h, flat.data_ptr() if flat.numel() else None, lens.ctypes.data,
+                                            id_arr.ctypes.data, clamp.ctypes.data, n, _stream(self.device)))
+        if payloads is not None:
+            if len(payloads) != n:
+                raise ValueError("payloads must have one entry per page")
+            for i, pay in zip(id_arr.tolist(), payloads):
+                self.payloads[i] = pay
+        return id_arr
+
+    def add_from_hidden(self, hidden: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
+                        attention_mask: torch.Tensor, ids: Optional[Sequence[int]] = None,
+                        payloads: Optional[Sequence[Any]] = None) -> np.ndarray:
+        """Ingestion fusion: encoder hidden states ``[B, S, H]`` -> fused projection + L2-normalise +
+        mask (K3) -> ragged page store, in HBM all the way (replaces ``embedding.tolist()`` + HTTP upsert,
+        functions.py:843-865)."""
+        from .head import project_normalize
+
+        emb = project_normalize(hidden.to(self.device), weight, bias, attention_mask)
+        return self.add_padded(emb, attention_mask.to(self.device), ids=ids, payloads=payloads)
+
     def fill_synthetic(self, n_pages: int, page_len: Union[int, Sequence[int]], seed: int, id_base: int = 0) -> None:
         """Append unit-norm pseudo-random pages generated on the device (benchmarks; see lis.h)."""
         lens = None

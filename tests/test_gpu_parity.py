@@ -521,3 +521,43 @@ def test_error_paths_and_limits(lis, oracle):
     assert torch.equal(gi.cpu(), wi) and torch.equal(gv.cpu(), wv)
     with pytest.raises(ValueError, match="out must be"):
         lis.score_multi_vector(q, p, out=torch.empty(3, 5))
+
+
+# ---------------------------------------------------------------------------------------------
+def test_padded_ingestion_drops_pad_rows_bit_identically(lis, oracle):
+    """add_padded stores no pad rows yet scores exactly like the reference on the padded tensor
+    (left padding = ColQwen, right padding = ColPali)."""
+    g = torch.Generator().manual_seed(19)
+    B, S = 24, 70
+    emb = rand_unit(g, B, S, 128)
+    mask = torch.ones(B, S, dtype=torch.long)
+    for i in range(B):
+        n_pad = int(torch.randint(0, 50, (1,), generator=g))
+        if i % 2:
+            mask[i, :n_pad] = 0            # left padding
+        else:
+            mask[i, S - n_pad:] = 0        # right padding
+    mask[3] = 1                            # one page without padding: must NOT be clamped
+    emb = emb * mask.unsqueeze(-1).to(emb.dtype)
+    q = rand_unit(g, 4, 16, 128)
+    q[2, :5] = -emb[3, :5]                 # make some per-token maxima negative
+    want = oracle.score_multi_vector_widened(q, emb)            # the reference on the padded tensor
+    idx = lis.LateInteractionIndex(B * S, B)
+    idx.add_padded(emb.cuda(), mask.cuda())
+    assert idx.num_rows == int(mask.sum())                       # no pad rows in HBM
+    got = idx.scores(q).cpu()
+    assert (got - want).abs().max().item() <= TOL_F32
+    padded = lis.score_multi_vector(q, emb, round_mode="f32")    # streaming the zero rows instead
+    assert torch.equal(got, padded)
+    idx.close()
+    # fused ingestion from hidden states
+    H = 256
+    hidden = torch.randn(B, S, H, generator=g).to(torch.bfloat16)
+    w = (torch.randn(128, H, generator=g) / 16).to(torch.bfloat16)
+    b = (0.05 * torch.randn(128, generator=g)).to(torch.bfloat16)
+    idx = lis.LateInteractionIndex(B * S, B)
+    idx.add_from_hidden(hidden.cuda(), w.cuda(), b.cuda(), mask.cuda())
+    e_ref = lis.project_normalize(hidden.cuda(), w.cuda(), b.cuda(), mask.cuda()).cpu()
+    want = oracle.score_multi_vector_widened(q, e_ref)
+    assert (idx.scores(q).cpu() - want).abs().max().item() <= TOL_F32
+    idx.close()
