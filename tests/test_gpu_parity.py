@@ -561,3 +561,37 @@ def test_padded_ingestion_drops_pad_rows_bit_identically(lis, oracle):
     want = oracle.score_multi_vector_widened(q, e_ref)
     assert (idx.scores(q).cpu() - want).abs().max().item() <= TOL_F32
     idx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+def test_full_size_config2_properties(lis, oracle):
+    """BASELINE configs[1] at full size (32 queries x 20 tokens vs 100 000 pages x 1030 tokens, 26 GB):
+    size-independent properties + oracle spot checks on pages read back from the store."""
+    pages, ptok = 100_000, 1030
+    idx = lis.LateInteractionIndex(pages * ptok, pages)
+    idx.fill_synthetic(pages, ptok, seed=2002)
+    g = torch.Generator().manual_seed(1002)
+    q = rand_unit(g, 32, 20, 128)
+    s1 = idx.scores(q)
+    s2 = idx.scores(q)
+    assert torch.equal(s1, s2)                                           # deterministic
+    assert torch.isfinite(s1).all() and s1.shape == (32, pages)
+    perm = torch.randperm(20, generator=g)
+    s3 = idx.scores(q[:, perm])                                          # sum over query tokens is order-free ...
+    assert (s3 - s1).abs().max().item() <= 1e-4                          # ... up to fp32 summation order
+    # oracle on randomly chosen pages (rows copied back from HBM), incl. the first and the last page
+    pick = [0, pages - 1] + torch.randint(1, pages - 1, (30,), generator=g).tolist()
+    sub = torch.stack([idx.read_rows(p * ptok, ptok) for p in pick])
+    want = oracle.score_multi_vector_widened(q, sub)
+    got = s1[:, pick].cpu()
+    assert (got - want).abs().max().item() <= TOL_F32
+    # top-k: sorted, consistent with the matrix, identical to the oracle's rule on the full rows
+    v, i = idx.search(q, 10)
+    assert (v[:, :-1] >= v[:, 1:]).all()
+    assert torch.equal(v, torch.gather(s1.cpu(), 1, i))
+    wv, wi = oracle.topk(s1.cpu(), 10)
+    assert torch.equal(i, wi) and torch.equal(v, wv)
+    # reference-rounding mode stays within one bf16 step of the fp32 result everywhere
+    s16 = idx.scores(q, round_mode="reference")
+    assert ((s16 - s1).abs() <= 2 * bf16_step(s1)).all()
+    idx.close()
