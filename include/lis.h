@@ -62,8 +62,9 @@ int lis_device_supported(int device);
  *
  * Queries are ragged lists of token rows, stored back to back ("packed rows": query q owns rows
  * [sum(len[<q]), sum(len[<=q]))).  The kernel reduces over rows inside one 128-row M tile, so a
- * query is cut into "segments" wherever it crosses a multiple of 128 rows; the partial sums of a cut
- * query are added by lis_reduce_segments.  lis_plan_queries computes that segmentation.
+ * query is cut into "segments" wherever it crosses a multiple of 64 rows (the CTA-pair kernel splits
+ * the last M tile of an odd pass 64/64 rows over two SMs); the partial sums of a cut query are added
+ * by lis_reduce_segments.  lis_plan_queries computes that segmentation.
  *   q_lens[nq]                tokens per query (>= 0; a 0-length query owns no segment, score 0)
  *   seg_query[cap]            out: owning query of each segment
  *   seg_lo[cap], seg_hi[cap]  out: packed row range [lo, hi) of the segment (inside one M tile)
@@ -120,10 +121,13 @@ int lis_reduce_segments(const float* seg_scores, int64_t ld_seg, const int32_t* 
 
 /* Tuning / debug knobs (process-wide); 0 always means "auto", and the defaults are what ships.
  *   tile_n     {0, 128, 192, 256}  page-token rows per MMA tile
- *   group      {0, 1..5}           query M tiles resident per pass over the page store
+ *   group      {0, 1..7}           query M tiles resident per pass over the page store (6, 7: CTA pairs only)
  *   max_ctas   0 = one per SM
  *   epi_halves {0, 1, 2}           4 or 8 epilogue warps
- *   a_operand  {0, 1, 2}           query operand of the MMA in shared memory (1) or tensor memory (2) */
+ *   a_operand  {0, 1, 2, 3}        query operand of the MMA in shared memory (1) or tensor memory (2) on one
+ *                                  CTA per SM, or 3 = CTA pairs (clusters of 2, tcgen05 cta_group::2: every page
+ *                                  tile is loaded once per pair and shared by up to 7 query tiles).  Auto: pairs
+ *                                  whenever a pass holds >= 2 query tiles, one CTA per SM for a single tile. */
 int lis_set_tuning(int tile_n, int group, int max_ctas, int epi_halves, int a_operand);
 /* Timing experiments only (scores become invalid): 1 = K1's epilogue skips the TMEM read-out, 2 = it skips
  * the max arithmetic, 3 = the producer issues no TMA loads after the first ring fill (stale tiles are reused),
@@ -141,6 +145,11 @@ int64_t lis_launch_count(void);
  * (a_in_tmem selects the TS form). */
 int lis_debug_sim_tile(const void* q, int64_t q_rows, const void* tokens, int64_t n_rows, int dtype,
                        int tile_n, int a_in_tmem, float* out, void* stream);
+/* Same for the CTA-pair form (cta_group::2): raw similarities of n_mt (3 or 4) query M tiles against the
+ * first 256 token rows, out[n_mt * 128, 256].  n_mt = 3 ends with the 64/64-split M = 128 instruction, so
+ * the dump pins both accumulator layouts. */
+int lis_debug_sim_pair(const void* q, int64_t q_rows, const void* tokens, int64_t n_rows, int dtype, int n_mt,
+                       float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K2: per-query top-k over a score matrix, deterministic order (score desc, id asc).

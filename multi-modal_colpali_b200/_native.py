@@ -49,6 +49,7 @@ SIGNATURES = {
     "lis_set_ablation": (_i32, [_i32]),
     "lis_k1_stats": (_i32, [_vp]),
     "lis_debug_sim_tile": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "lis_debug_sim_pair": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp]),
     "lis_topk_workspace_bytes": (_i64, [_i64, _i64, _i32]),
     "lis_topk": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp]),
     "lis_merge_topk": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp]),

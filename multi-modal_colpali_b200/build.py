@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "_lib"
 LIB = LIBDIR / "liblis.so"
-SOURCES = ["lis_maxsim.cu", "lis_topk.cu", "lis_project.cu", "lis_index.cu"]
+SOURCES = ["lis_maxsim.cu", "lis_maxsim_pair.cu", "lis_topk.cu", "lis_project.cu", "lis_index.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-DLIS_BUILD",

@@ -10,6 +10,9 @@
 
 namespace lis {
 
+// Queries are cut into segments at multiples of 64 packed rows: an M tile holds 128 rows, and the CTA-pair
+// kernel splits the last tile of an odd pass 64/64 over two SMs (each sums the segments of its half).
+constexpr int kSegCut = 64;
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -140,6 +143,10 @@ static int dispatch_maxsim(int nt, int g, bool atm, const Maps& m, const MaxSimA
   return LIS_E_INVALID;
 }
 
+// CTA-pair form (lis_maxsim_pair.cu)
+int dispatch_maxsim_pair(const CUtensorMap& q, const CUtensorMap& p, const MaxSimArgs& a, int grid, cudaStream_t st,
+                         bool dbg);
+
 static int max_group(int nt, bool atm) {
   if (atm) return nt == 128 ? 4 : (nt == 192 ? 2 : 0);
   return nt == 256 ? 3 : (nt == 128 ? 5 : 0);
@@ -176,16 +183,20 @@ int lis_device_supported(int device) {
 
 int lis_set_tuning(int tile_n, int group, int max_ctas, int epi_halves, int a_operand) {
   LIS_REQUIRE(tile_n == 0 || tile_n == 128 || tile_n == 192 || tile_n == 256, "tile_n must be 0, 128, 192 or 256");
-  LIS_REQUIRE(a_operand >= 0 && a_operand <= 2, "a_operand must be 0 (auto), 1 (shared memory) or 2 (tensor memory)");
+  LIS_REQUIRE(a_operand >= 0 && a_operand <= 3,
+              "a_operand must be 0 (auto), 1 (shared memory), 2 (tensor memory) or 3 (CTA pairs)");
   LIS_REQUIRE(epi_halves >= 0 && epi_halves <= 2, "epi_halves must be 0 (auto), 1 or 2");
   LIS_REQUIRE(max_ctas >= 0, "max_ctas must be >= 0");
-  LIS_REQUIRE(group >= 0 && group <= 5, "group must be in 0..5");
-  if (tile_n && a_operand) {
+  LIS_REQUIRE(group >= 0 && group <= 7, "group must be in 0..7");
+  LIS_REQUIRE(a_operand == 3 || (a_operand == 0 && tile_n == 0) || group <= 5, "group > 5 needs the CTA-pair form");
+  LIS_REQUIRE(a_operand != 3 || group == 0 || group >= 2, "the CTA-pair form keeps 2..7 query tiles per pass");
+  LIS_REQUIRE(a_operand != 3 || tile_n == 0 || tile_n == 256, "the CTA-pair form uses 256-row page tiles");
+  if (tile_n && a_operand && a_operand != 3) {
     const int gm = max_group(tile_n, a_operand == 2);
     LIS_REQUIRE(gm > 0, "tile_n=%d is not available with a_operand=%d", tile_n, a_operand);
     LIS_REQUIRE(group <= gm, "tile_n=%d a_operand=%d supports group <= %d", tile_n, a_operand, gm);
   }
-  LIS_REQUIRE(!(tile_n == 256 && group > 3), "tile_n=256 supports group <= 3");
+  LIS_REQUIRE(!(tile_n == 256 && group > 3 && a_operand != 3), "tile_n=256 supports group <= 3 on a single CTA");
   g_tuning.tile_n = tile_n;
   g_tuning.group = group;
   g_tuning.max_ctas = max_ctas;
@@ -210,7 +221,7 @@ int64_t lis_plan_queries(const int32_t* q_lens, int64_t nq, int64_t cap, int32_t
       return LIS_E_INVALID;
     }
     while (len > 0) {
-      const int64_t room = kMTile - (row % kMTile);  // rows left in the current M tile
+      const int64_t room = kSegCut - (row % kSegCut);  // rows left before the next cut
       const int64_t take = std::min<int64_t>(len, room);
       if (write) {
         if (n_seg >= cap) {
@@ -334,26 +345,57 @@ static int maxsim_impl(const void* q, const void* q_lo, int64_t q_rows, const in
   bool atm;
   if (planes == 2) { nt = 128; g = 1; atm = false; }
   else choose_tiling(n_mtiles, &nt, &g, &atm);
-  Maps m;
-  int rc = encode_rows_tmap(&m.q, q, q_rows, kMTile, dtype);
-  if (rc) return rc;
-  // an empty token store still needs a valid map: point it at the query rows (never loaded)
-  rc = n_rows > 0 ? encode_rows_tmap(&m.p, tokens, n_rows, nt, dtype) : encode_rows_tmap(&m.p, q, q_rows, nt, dtype);
-  if (rc) return rc;
-  m.q2 = m.q;
-  m.p2 = m.p;
-  if (planes == 2) {
-    rc = encode_rows_tmap(&m.q2, q_lo, q_rows, kMTile, dtype);
+  // CTA pairs (cta_group::2) whenever two or more query tiles share a pass over the store: the pair reads
+  // every page tile once for up to 7 query tiles.  A single tile is HBM-bound and stays on one CTA per SM.
+  const bool want_pair = g_tuning.a_operand == 3 || (g_tuning.a_operand == 0 && g_tuning.tile_n == 0);
+  const bool pair = planes == 1 && want_pair && n_mtiles >= 2 && n_rows > 0 && g_tuning.group != 1 && sms >= 2;
+  if (pair) {
+    const int gmax = g_tuning.group ? std::min(std::max(g_tuning.group, 2), 7) : 6;
+    const int64_t passes = (n_mtiles + gmax - 1) / gmax;
+    g = (int)((n_mtiles + passes - 1) / passes);
+    nt = 256;
+    atm = false;
+  }
+  Maps m;   // single-CTA form: 128-row query box, nt-row page box
+  Maps mp;  // pair form: 64-row query box, 128-row page box
+  bool have_single = false;
+  auto single_maps = [&]() -> int {
+    if (have_single) return LIS_OK;
+    int rc = encode_rows_tmap(&m.q, q, q_rows, kMTile, dtype);
     if (rc) return rc;
-    if (n_rows > 0) {
-      rc = encode_rows_tmap(&m.p2, tokens_lo, n_rows, nt, dtype);
+    // an empty token store still needs a valid map: point it at the query rows (never loaded)
+    rc = n_rows > 0 ? encode_rows_tmap(&m.p, tokens, n_rows, nt, dtype) : encode_rows_tmap(&m.p, q, q_rows, nt, dtype);
+    if (rc) return rc;
+    m.q2 = m.q;
+    m.p2 = m.p;
+    if (planes == 2) {
+      rc = encode_rows_tmap(&m.q2, q_lo, q_rows, kMTile, dtype);
       if (rc) return rc;
+      if (n_rows > 0) {
+        rc = encode_rows_tmap(&m.p2, tokens_lo, n_rows, nt, dtype);
+        if (rc) return rc;
+      }
     }
+    have_single = true;
+    return LIS_OK;
+  };
+  int rc = LIS_OK;
+  if (pair) {
+    rc = encode_rows_tmap(&mp.q, q, q_rows, 64, dtype);
+    if (rc) return rc;
+    rc = encode_rows_tmap(&mp.p, tokens, n_rows, 128, dtype);
+    if (rc) return rc;
+  } else {
+    rc = single_maps();
+    if (rc) return rc;
   }
 
   int grid = sms;
   if (g_tuning.max_ctas > 0) grid = std::min(grid, g_tuning.max_ctas);
   grid = (int)std::min<int64_t>(grid, std::max<int64_t>(np, 1));
+  int grid_pair = sms & ~1;
+  if (g_tuning.max_ctas > 0) grid_pair = std::max(2, std::min(grid_pair, g_tuning.max_ctas & ~1));
+  grid_pair = (int)std::min<int64_t>(grid_pair, 2 * std::max<int64_t>(np, 1));
 
   for (int64_t mt0 = 0; mt0 < n_mtiles; mt0 += g) {
     MaxSimArgs a;
@@ -374,8 +416,14 @@ static int maxsim_impl(const void* q, const void* q_lo, int64_t q_rows, const in
     a.is_bf16 = dtype == LIS_BF16;
     a.ablate = g_tuning.ablate;
     a.stats = g_stats;
-    // the instantiation whose group equals this pass's tile count (the last pass may be short)
-    rc = dispatch_maxsim(nt, a.n_mt, atm, m, a, grid, st, false, planes);
+    if (pair && a.n_mt >= 2) {
+      rc = dispatch_maxsim_pair(mp.q, mp.p, a, grid_pair, st, false);
+    } else {
+      // the instantiation whose group equals this pass's tile count (the last pass may be short)
+      rc = single_maps();
+      if (rc) return rc;
+      rc = dispatch_maxsim(nt, a.n_mt, atm, m, a, grid, st, false, planes);
+    }
     if (rc) return rc;
   }
   return LIS_OK;
@@ -473,6 +521,49 @@ int lis_debug_sim_tile(const void* q, int64_t q_rows, const void* tokens, int64_
   a.q = q;
   a.q_rows = q_rows;
   rc = dispatch_maxsim(tile_n, 1, a_in_tmem != 0, m, a, 1, st, true);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(scratch);
+  if (rc) return rc;
+  LIS_CUDA_CHECK(e);
+  return LIS_OK;
+}
+
+
+namespace {
+__global__ void fill_pair_debug_tables(int64_t* off, int32_t* mt_seg, int64_t rows, int n_mt) {
+  off[0] = 0; off[1] = rows;                       // one page covering all rows
+  for (int t = 0; t <= n_mt; ++t) mt_seg[t] = 0;   // no segments: nothing is written but the dump
+}
+}  // namespace
+
+int lis_debug_sim_pair(const void* q, int64_t q_rows, const void* tokens, int64_t n_rows, int dtype, int n_mt,
+                       float* out, void* stream) {
+  LIS_REQUIRE(q && tokens && out, "lis_debug_sim_pair: null pointer");
+  LIS_REQUIRE(n_mt == 3 || n_mt == 4, "lis_debug_sim_pair: n_mt must be 3 or 4");
+  LIS_REQUIRE(q_rows > (int64_t)(n_mt - 1) * kMTile && q_rows <= (int64_t)n_mt * kMTile && n_rows > 0,
+              "lis_debug_sim_pair: q_rows must fill %d M tiles and the store must not be empty", n_mt);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap mq, mp;
+  int rc = encode_rows_tmap(&mq, q, q_rows, 64, dtype);
+  if (rc) return rc;
+  rc = encode_rows_tmap(&mp, tokens, n_rows, 128, dtype);
+  if (rc) return rc;
+  char* scratch = nullptr;
+  LIS_CUDA_CHECK(cudaMalloc(&scratch, 256));
+  int64_t* off = (int64_t*)scratch;
+  int32_t* mt_seg = (int32_t*)(scratch + 64);
+  float* dummy = (float*)(scratch + 128);
+  fill_pair_debug_tables<<<1, 1, 0, st>>>(off, mt_seg, std::min<int64_t>(n_rows, 256), n_mt);
+  count_launch();
+  MaxSimArgs a;
+  a.p_offsets = off; a.p_clamp = nullptr; a.seg_lo = mt_seg; a.seg_hi = mt_seg; a.mt_seg = mt_seg;
+  a.out = dummy; a.dbg = out; a.ld_out = 1; a.np = 1; a.mt0 = 0; a.n_mt = n_mt; a.round_mode = 0;
+  a.is_bf16 = dtype == LIS_BF16;
+  a.ablate = 0;
+  a.stats = nullptr;
+  a.q = q;
+  a.q_rows = q_rows;
+  rc = dispatch_maxsim_pair(mq, mp, a, 2, st, true);
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(scratch);
   if (rc) return rc;

@@ -132,6 +132,60 @@ __device__ __forceinline__ int64_t lower_bound_off(const int64_t* off, int64_t n
   return lo;
 }
 
+// Page reducer body shared by the single-CTA and the CTA-pair kernel: one finished (page, M tile) sits in
+// shared memory as `nparts` column partitions of partial row maxima (row r of partition c at ex[c * pstride + r]);
+// combine the partitions (max), clamp / round like the reference, and add up the rows of every query segment
+// of the tile -> one fp32 per (segment, page).  The warp is cut into groups of G = 32 / 2^ceil(log2(seg_cnt))
+// lanes, one group per segment (all segments of a typical tile in one round): a group strides over the
+// segment's rows and finishes with a log2(G)-step shuffle tree.  The order of the additions depends only on
+// the tile's segment table, so every kernel form produces the same bits.
+// [rbase, rbase + rcnt): tile rows this CTA owns (the whole tile, or 64 rows of a split tile: segments of the
+// other half are skipped; a segment straddling the boundary is a planning error and traps).
+__device__ __forceinline__ void reduce_tile_segments(const float* ex, int nparts, int pstride, const uint16_t* tab16,
+                                                     const int32_t* g_lo, const int32_t* g_hi, int seg_first, int seg_cnt,
+                                                     int tile_row0, int rbase, int rcnt, bool clamp, bool round_ref,
+                                                     bool round_sum, int is_bf16, float* out_col, int64_t ld_out,
+                                                     int lane) {
+  int per_round = 1;
+  while (per_round < seg_cnt && per_round < 32) per_round <<= 1;
+  const int G = 32 / per_round;
+  const int sub = lane & (G - 1), which = lane / G;
+  for (int j0 = 0; j0 < seg_cnt; j0 += per_round) {
+    const int j = j0 + which;
+    int lo = 0, hi = 0;
+    bool mine = false;
+    if (j < seg_cnt) {
+      if (j < 16) {
+        const uint32_t lh = tab16[j];
+        lo = (int)(lh & 0xffu); hi = (int)(lh >> 8);
+      } else {
+        lo = __ldg(g_lo + seg_first + j) - tile_row0;
+        hi = __ldg(g_hi + seg_first + j) - tile_row0;
+      }
+      lo -= rbase; hi -= rbase;
+      mine = hi > 0 && lo < rcnt;
+      if (mine && (lo < 0 || hi > rcnt)) {
+        printf("lis: a query segment straddles the 64-row midpoint of the M tile at row %d (plan with lis_plan_queries)\n", tile_row0);
+        __trap();
+      }
+      if (!mine) { lo = 0; hi = 0; }
+    }
+    float acc = 0.f;
+    for (int r = lo + sub; r < hi; r += G) {
+      float x = ex[r];
+      for (int c = 1; c < nparts; ++c) x = fmaxf(x, ex[c * pstride + r]);
+      if (clamp) x = fmaxf(x, 0.f);
+      if (round_ref) x = round_to_input_dtype(x, is_bf16);
+      acc += x;
+    }
+    for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (mine && sub == 0) {
+      if (round_sum) acc = round_to_input_dtype(acc, is_bf16);
+      out_col[(int64_t)(seg_first + j) * ld_out] = acc;
+    }
+  }
+}
+
 // ATM ("A in tensor memory"): the query M tiles are stored in TMEM (64 columns each, two 16-bit
 // values per 32-bit cell) and the MMA takes its A operand from there (TS form).  Shared memory then
 // serves only the page tiles: the SS form at M=128 x N=256 reads 96 B/clk of operands from smem,
@@ -364,30 +418,8 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         const float* ex = srm + slot * (EH * kMTile);
         const int mt = args.mt0 + g;
         const int seg_first = seginfo[2 * g], seg_cnt = seginfo[2 * g + 1];
-        for (int j = 0; j < seg_cnt; ++j) {
-          int lo, hi;
-          if (j < 16) {
-            const uint32_t lh = segtab[g * 16 + j];
-            lo = (int)(lh & 0xffu); hi = (int)(lh >> 8);
-          } else {
-            lo = __ldg(args.seg_lo + seg_first + j) - mt * kMTile;
-            hi = __ldg(args.seg_hi + seg_first + j) - mt * kMTile;
-          }
-          float acc = 0.f;
-          for (int r = lo + lane; r < hi; r += 32) {
-            float x = ex[r];
-            if (EH == 2) x = fmaxf(x, ex[kMTile + r]);
-            if (clamp) x = fmaxf(x, 0.f);
-            if (round_ref) x = round_to_input_dtype(x, is_bf16);
-            acc += x;
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-          if (lane == 0) {
-            if (round_sum) acc = round_to_input_dtype(acc, is_bf16);
-            args.out[(int64_t)(seg_first + j) * args.ld_out + p] = acc;
-          }
-        }
+        reduce_tile_segments(ex, EH, kMTile, segtab + g * 16, args.seg_lo, args.seg_hi, seg_first, seg_cnt, mt * kMTile, 0,
+                             kMTile, clamp, round_ref, round_sum, is_bf16, args.out + p, args.ld_out, lane);
         __syncwarp();
         if (lane == 0) mbar_arrive(ex_empty + slot);
       }

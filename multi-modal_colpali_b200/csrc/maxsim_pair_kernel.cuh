@@ -1,0 +1,507 @@
+// K1P: the fused MaxSim kernel on CTA PAIRS (thread-block clusters of 2, tcgen05 cta_group::2).
+//
+// Same arithmetic and the same flat page tiling as maxsim_kernel.cuh (reference: score_multi_vector,
+// 05_experiment02.py:214; einsum("bnd,csd->bcns").max(3).sum(2), HF processing_colpali.py:360), but
+// two SMs work on every 256-row page tile together:
+//
+//   * each CTA of the pair TMA-loads HALF of the page tile (128 rows, 32 KB) -- the pair reads the
+//     page store ONCE for up to 7 query M tiles (a single CTA can keep 3 resident), and the 32 KB
+//     stages leave room for a 3..6-deep TMA ring next to the resident queries;
+//   * one elected thread of the leader CTA issues tcgen05.mma.cta_group::2: D[256 x 256] = A[256 x 128] B^T,
+//     CTA r supplying query tile (2u + r) as its half of A and reading both halves of B.  Operand
+//     fetch drops from 96 to 64 B/clk per SM, so TMA writes no longer compete with the tensor pipe;
+//   * an ODD tile count ends with one M = 128 instruction per k-step: the last query tile is split
+//     64/64 rows over the pair, at full tensor rate (no padded tile).  Its accumulator sits in
+//     TMEM as lanes 0-63 = rows x columns [0,128), lanes 64-127 = the same rows x columns [128,256)
+//     (the "2x2" layout of cute's tmem_frg_2sm<M_MMA=64>).
+//
+// Each CTA owns the scores of ITS query rows for all pages of the pair's range, so every output
+// element still has exactly one writer.  Segments must not straddle the 64-row midpoint of a tile
+// (lis_plan_queries cuts there).
+#pragma once
+#include "maxsim_kernel.cuh"
+
+namespace lis {
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster_u32(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on an mbarrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar_cluster,
+                                                 int32_t c0, int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in both CTAs once the MMAs issued so far are done
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+constexpr int kPairTail = 3072;   // bytes of barriers / tables behind the operand stages
+constexpr int kPairWindow = 64;   // page-table window (pages)
+
+// NF: uses with M = 256 (two query tiles, one per CTA); ODD: a final use with M = 128 (one tile, 64 rows per CTA).
+template <int NF, bool ODD, bool DBG>
+__global__ void __launch_bounds__(kCtrlThreads + 256, 1)
+maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_p,
+                   const MaxSimArgs args, const int NS) {
+  constexpr int NT = 256;                 // page rows per tile (N of the MMA)
+  constexpr int EH = 2;                   // two epilogue warps per TMEM lane quarter
+  constexpr int U = NF + (ODD ? 1 : 0);   // uses (accumulator hand-overs) per page tile
+  constexpr int NACC = 2;
+  constexpr int kAFull = kMTile * kDim * 2;        // 32 KB: this CTA's tile of an M = 256 use
+  constexpr int kAHalfTile = 64 * kDim * 2;        // 16 KB: this CTA's 64 rows of the split tile
+  constexpr int kABytes = NF * kAFull + (ODD ? kAHalfTile : 0);
+  constexpr int kBRows = NT / 2;                   // page rows of a tile held by this CTA
+  constexpr int kBStage = kBRows * kDim * 2;       // 32 KB
+  constexpr int kBHalf = kBRows * 128;             // one K half (64 elements) of the stage
+  constexpr int kPW = kPairWindow;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kABytes;
+  uint8_t* tail = smem_b + (size_t)NS * kBStage;
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(tail);      // 1   (leader's is used)
+  uint64_t* b_full = q_full + 1;                             // [8] (leader's are used)
+  uint64_t* b_empty = b_full + 8;                            // [8] per CTA
+  uint64_t* acc_full = b_empty + 8;                          // [2] per CTA
+  uint64_t* acc_empty = acc_full + 2;                        // [2] (leader's are used; both CTAs' warps arrive)
+  uint64_t* ex_full = acc_empty + 2;                         // [2]
+  uint64_t* ex_empty = ex_full + 2;                          // [2]
+  int64_t* ex_meta = reinterpret_cast<int64_t*>(ex_empty + 2);   // [2][2]
+  int64_t* range = ex_meta + 4;                                  // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(range + 4);  // [2]
+  float* srm = reinterpret_cast<float*>(tmem_slot + 2);          // [2][256]
+  int32_t* pw_end = reinterpret_cast<int32_t*>(srm + 2 * EH * kMTile);   // [kPW]
+  int32_t* seginfo = pw_end + kPW;                                      // [U][2]
+  uint16_t* segtab = reinterpret_cast<uint16_t*>(seginfo + 2 * U);      // [U][16]
+  uint8_t* pw_clamp = reinterpret_cast<uint8_t*>(segtab + 16 * U);      // [kPW]
+  static_assert((1 + 8 + 8 + 2 + 2 + 2 + 2 + 4 + 4) * 8 + 8 + 2 * EH * kMTile * 4 + kPW * 4 + U * 8 + U * 32 + kPW <=
+                    kPairTail, "tail does not fit");
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int kReducerWarp = 4 * EH;
+  constexpr int kProducerWarp = 4 * EH + 1;
+  constexpr int kMmaWarp = 4 * EH + 2;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int mt_split = args.mt0 + 2 * NF;       // the tile shared 64/64 by the pair (ODD only)
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_p);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < NS; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, kMmaWarps); }
+    for (int a = 0; a < NACC; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, 2 * 4 * EH); }
+    for (int i = 0; i < 2; ++i) { mbar_init(ex_full + i, 4 * EH); mbar_init(ex_empty + i, 1); }
+    fence_barrier_init();
+    // The PAIR's contiguous range of whole pages, balanced by token rows.
+    const int64_t np = args.np;
+    const int64_t cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+    const int64_t base = __ldg(args.p_offsets);
+    const int64_t total = __ldg(args.p_offsets + np) - base;
+    const int64_t per = (total + ncl - 1) / ncl;
+    int64_t pa = np, pb = np;
+    if (per > 0 && cid * per < total) {
+      pa = lower_bound_off(args.p_offsets, np, base + cid * per);
+      pb = (cid + 1 == ncl || (cid + 1) * per >= total) ? np : lower_bound_off(args.p_offsets, np, base + (cid + 1) * per);
+    } else if (total == 0 && cid == 0) {
+      pa = 0; pb = np;
+    }
+    range[0] = pa;
+    range[1] = pb;
+    range[2] = (pa < np) ? __ldg(args.p_offsets + pa) : 0;
+    range[3] = (pa < pb) ? __ldg(args.p_offsets + pb) : range[2];
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc_pair(tmem_slot, kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();        // both CTAs' barriers are initialised before anyone signals across the pair
+  tc_fence_after();
+
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t pa = range[0], pb = range[1];
+  const int64_t row0 = range[2];
+  const int64_t rows = range[3] - row0;
+  const int ntiles = (int)((rows + NT - 1) / NT);
+
+  if (warp == kProducerWarp) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (pa < pb && ntiles > 0) {
+      const uint32_t q_full_l = mapa_u32(smem_u32(q_full), 0);
+      const uint32_t b_full_l = mapa_u32(smem_u32(b_full), 0);
+      if (elect_one_sync()) {
+        if (leader) mbar_arrive_expect_tx(q_full, 2u * kABytes);
+        const uint32_t a0 = smem_u32(smem_a);
+        for (int u = 0; u < NF; ++u)
+          for (int h = 0; h < 2; ++h)
+            for (int j = 0; j < 2; ++j)
+              tma_load_2d_pair(a0 + u * kAFull + h * (kMTile * 128) + j * 8192, &tmap_q, q_full_l, h * kKHalf,
+                               (args.mt0 + 2 * u + (int)rank) * kMTile + j * 64, kPolicyEvictLast);
+        if (ODD)
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d_pair(a0 + NF * kAFull + h * 8192, &tmap_q, q_full_l, h * kKHalf,
+                             mt_split * kMTile + (int)rank * 64, kPolicyEvictLast);
+      }
+      __syncwarp();
+      const uint32_t b0 = smem_u32(smem_b);
+      const bool st_on = LIS_STATS_ON(args) && blockIdx.x < 2;
+      long long st_wait = 0;
+      const long long st_t0 = clock64();
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t % NS;
+        const uint32_t ph = (uint32_t)(t / NS) & 1u;
+        const long long c0 = st_on ? clock64() : 0;
+        mbar_wait(b_empty + s, ph ^ 1u);
+        if (st_on) st_wait += clock64() - c0;
+        if (elect_one_sync()) {
+          if (leader) mbar_arrive_expect_tx(b_full + s, 2u * kBStage);
+          const uint32_t dst = b0 + (uint32_t)s * kBStage;
+          const int32_t r = (int32_t)(row0 + (int64_t)t * NT) + (int32_t)rank * kBRows;
+          tma_load_2d_pair(dst, &tmap_p, b_full_l + s * 8, 0, r, kPolicyEvictFirst);
+          tma_load_2d_pair(dst + kBHalf, &tmap_p, b_full_l + s * 8, kKHalf, r, kPolicyEvictFirst);
+        }
+        __syncwarp();
+      }
+      // tail: every release of a stage (a multicast commit issued by the leader) has landed here before
+      // this CTA may leave -- wait for the hand-back of the last tile that used each stage
+      if (st_on && lane == 0) {
+        args.stats[rank * 64 + 24] = st_wait;              // producer: waiting for a free stage
+        args.stats[rank * 64 + 25] = clock64() - st_t0;    //           whole loop
+      }
+      for (int t = ntiles; t < ntiles + NS; ++t)
+        if (t >= NS) mbar_wait(b_empty + t % NS, ((uint32_t)(t / NS) & 1u) ^ 1u);
+    }
+  } else if (warp >= kMmaWarp) {
+    // ===================== MMA issuers (leader CTA only) =====================
+    if (leader && pa < pb && ntiles > 0) {
+      const uint32_t fmt = args.is_bf16 ? 1u : 0u;
+      const uint32_t idesc_full = make_idesc_f16(fmt, 256, NT);
+      const uint32_t idesc_split = make_idesc_f16(fmt, 128, NT);
+      const uint32_t a_base = smem_u32(smem_a);
+      const uint32_t b_base = smem_u32(smem_b);
+      const uint32_t acc_full_u = smem_u32(acc_full), b_empty_u = smem_u32(b_empty);
+      const uint32_t b_empty_peer = mapa_u32(b_empty_u, 1);
+      mbar_wait(q_full, 0);
+      uint32_t use = 0;
+      const uint32_t my = (uint32_t)(warp - kMmaWarp);
+      const bool st_on = LIS_STATS_ON(args) && blockIdx.x == 0 && my == 0;
+      long long st_b = 0, st_acc = 0, st_issue = 0;
+      const long long st_t0 = clock64();
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t % NS;
+        long long c0 = st_on ? clock64() : 0;
+        mbar_wait(b_full + s, (uint32_t)(t / NS) & 1u);
+        if (st_on) st_b += clock64() - c0;
+        tc_fence_after();
+        bool issued = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u, ++use) {
+          if (use % kMmaWarps != my) continue;
+          issued = true;
+          const uint32_t a = use & 1u;
+          c0 = st_on ? clock64() : 0;
+          mbar_wait(acc_empty + a, ((use >> 1) & 1u) ^ 1u);
+          const long long c1 = st_on ? clock64() : 0;
+          if (st_on) st_acc += c1 - c0;
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + a * NT;
+          const bool split = ODD && u == NF;
+          if (LIS_ISSUE_PRED) {
+#pragma unroll
+            for (int k = 0; k < kDim / 16; ++k) {
+              const uint32_t koff_a = (uint32_t)(k >> 2) * (split ? 8192u : (uint32_t)(kMTile * 128)) + (uint32_t)(k & 3) * 32;
+              const uint32_t koff_b = (uint32_t)(k >> 2) * kBHalf + (uint32_t)(k & 3) * 32;
+              const uint64_t adesc = make_kmajor_sw128_desc(a_base + u * kAFull + koff_a);
+              const uint64_t bdesc = make_kmajor_sw128_desc(b_base + s * kBStage + koff_b);
+              umma_f16_pair(d_tmem, adesc, bdesc, split ? idesc_split : idesc_full, k ? 1u : 0u);
+            }
+            umma_commit_pair(acc_full_u + a * 8);
+          }
+          __syncwarp();
+          if (st_on) st_issue += clock64() - c1;
+        }
+        // hand the page tile back to both producers once this warp's MMAs on it are done
+        if (LIS_ISSUE_PRED) {
+          if (issued) umma_commit_pair(b_empty_u + s * 8);
+          else { mbar_arrive_u32(b_empty_u + s * 8); mbar_arrive_cluster_u32(b_empty_peer + s * 8); }
+        }
+        __syncwarp();
+      }
+      if (st_on && lane == 0) {
+        args.stats[0] = clock64() - st_t0;   // MMA warp 0: whole loop
+        args.stats[1] = st_b;                //   waiting for page tiles
+        args.stats[2] = st_acc;              //   waiting for a free accumulator
+        args.stats[3] = use;
+        args.stats[23] = st_issue;           //   issuing MMAs + commit
+      }
+    }
+  } else if (warp == kReducerWarp) {
+    // ===================== page reducer (both CTAs, each for its own query rows) =====================
+    if (pa < pb) {
+      const int is_bf16 = args.is_bf16;
+      const bool round_ref = (args.round_mode & 1) != 0;
+      const bool round_sum = round_ref && (args.round_mode & 2) == 0;
+      const int64_t nfin = (pb - pa) * U;
+      for (int64_t f = 0; f < nfin; ++f) {
+        const int slot = (int)(f & 1);
+        mbar_wait(ex_full + slot, (uint32_t)(f >> 1) & 1u);
+        const int64_t p = ex_meta[2 * slot];
+        const int g = (int)(ex_meta[2 * slot + 1] & 0xff);
+        const bool clamp = (ex_meta[2 * slot + 1] >> 8) != 0;
+        const float* ex = srm + slot * (EH * kMTile);
+        const bool split = ODD && g == NF;
+        const int mt = split ? mt_split : args.mt0 + 2 * g + (int)rank;
+        const int rbase = split ? (int)rank * 64 : 0;       // first tile row this CTA owns in this use
+        const int rcnt = split ? 64 : kMTile;
+        const int seg_first = seginfo[2 * g], seg_cnt = seginfo[2 * g + 1];
+        reduce_tile_segments(ex, split ? 4 : 2, split ? 64 : kMTile, segtab + g * 16, args.seg_lo, args.seg_hi, seg_first,
+                             seg_cnt, mt * kMTile, rbase, rcnt, clamp, round_ref, round_sum, is_bf16, args.out + p,
+                             args.ld_out, lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ex_empty + slot);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 0..7, both CTAs) =====================
+    // M = 256 use: thread = query row (lane quarter * 32 + lane) of this CTA's tile; the two warps of a lane
+    // quarter scan tile columns [0,128) and [128,256).  Split use: lanes 0-63 hold this CTA's 64 rows x
+    // columns [0,128), lanes 64-127 the same rows x columns [128,256), so a warp scans 64 columns and four
+    // partial maxima per row meet in the exchange slot.
+    const int quarter = warp & 3;
+    const int half = warp >> 2;
+    const int etid = half * kMTile + quarter * 32 + lane;
+    float rm[U];
+#pragma unroll
+    for (int g = 0; g < U; ++g) rm[g] = -INFINITY;
+    auto rotate = [&](float cur) {
+#pragma unroll
+      for (int i = 0; i + 1 < U; ++i) rm[i] = rm[i + 1];
+      rm[U - 1] = cur;
+    };
+
+    const uint32_t acc_full_u = smem_u32(acc_full);
+    const uint32_t acc_empty_l = mapa_u32(smem_u32(acc_empty), 0);   // the leader's barrier, as a cluster address
+    const uint32_t ex_full_u = smem_u32(ex_full), ex_empty_u = smem_u32(ex_empty);
+    const int npages = (int)(pb - pa);
+
+    int w0 = 0;
+    auto refill = [&](int base) {
+      named_bar_sync(1, 128 * EH);
+      if (etid < kPW) {
+        const int pg = base + etid;
+        int e = 0;
+        uint8_t c = 0;
+        if (pg < npages) {
+          e = (int)(__ldg(args.p_offsets + pa + pg + 1) - row0);
+          if (args.p_clamp != nullptr) c = __ldg(args.p_clamp + pa + pg);
+        }
+        pw_end[etid] = e;
+        pw_clamp[etid] = c;
+      }
+      named_bar_sync(1, 128 * EH);
+      w0 = base;
+    };
+    if (etid < U * 16) {                       // segment tables of this CTA's tiles
+      const int g = etid >> 4, j = etid & 15;
+      const int mt = (ODD && g == NF) ? mt_split : args.mt0 + 2 * g + (int)rank;
+      const int first = __ldg(args.mt_seg + mt), cnt = __ldg(args.mt_seg + mt + 1) - first;
+      if (j == 0) { seginfo[2 * g] = first; seginfo[2 * g + 1] = cnt; }
+      if (j < cnt)
+        segtab[g * 16 + j] = (uint16_t)((__ldg(args.seg_lo + first + j) - mt * kMTile) |
+                                        ((__ldg(args.seg_hi + first + j) - mt * kMTile) << 8));
+    }
+
+    uint32_t fin = 0;
+    auto finish_page = [&](int g, int pi, float v) {
+      const uint32_t slot = fin & 1u;
+      mbar_wait_u32(ex_empty_u + slot * 8, ((fin >> 1) & 1u) ^ 1u);
+      srm[slot * (EH * kMTile) + etid] = v;
+      if (etid == 0) {
+        ex_meta[2 * slot] = pa + pi;
+        ex_meta[2 * slot + 1] = (int64_t)g | ((int64_t)pw_clamp[pi - w0] << 8);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_u32(ex_full_u + slot * 8);
+      ++fin;
+    };
+
+    long long st_wait = 0, st_hold = 0;
+    if (pa < pb) {
+      int p = 0;
+      refill(0);
+      int pend = pw_end[0];
+      uint32_t use = 0;
+      const long long st_t0 = clock64();
+      const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      for (int t = 0; t < ntiles; ++t) {
+        const int tcol = t * NT;
+        auto rel_end = [&](int e) { const int d = e - tcol; return d > NT ? NT + 1 : d; };
+        const int pe_tile = rel_end(pend);
+        int p_next = p, pend_next = pend;
+
+        // one use: SPLIT selects the M = 128 accumulator layout
+        auto do_use = [&](auto split_tag, const int g) {
+          constexpr bool SPLIT = decltype(split_tag)::value;
+          constexpr int NOWN = SPLIT ? 2 : 4;                        // 32-column chunks scanned by this warp
+          const int c_beg = SPLIT ? (quarter >> 1) * 128 + half * 64 : half * 128;   // its first tile column
+          const uint32_t a = use & 1u;
+          const bool st_on = LIS_STATS_ON(args) && blockIdx.x < 2;
+          const long long ec0 = st_on ? clock64() : 0;
+          mbar_wait_u32(acc_full_u + a * 8, (use >> 1) & 1u);
+          const long long ec1 = st_on ? clock64() : 0;
+          tc_fence_after();
+          ++use;
+          const uint32_t taddr = tlane + a * NT + (SPLIT ? half * 64 : half * 128);
+          int pp = p, ppend = pend;
+          bool live = pp < npages;
+          int pe = pe_tile;
+          float m = rm[0];
+
+          auto next_page = [&]() {
+            m = -INFINITY;
+            ++pp;
+            if (pp >= npages) { live = false; pe = NT + 1; return; }
+            if (pp >= w0 + kPW) refill(pp - p < kPW ? p : pp);
+            ppend = pw_end[pp - w0];
+            pe = rel_end(ppend);
+          };
+          auto skip_to = [&](int col_end) {
+            while (live && pe <= col_end) { finish_page(g, pp, m); next_page(); }
+          };
+          auto scan = [&](const uint32_t (&v)[32], int cb) {
+            if (DBG) {
+              if (blockIdx.x < 2 && t == 0 && args.dbg != nullptr) {
+                const int qrow = SPLIT ? mt_split * kMTile + (int)rank * 64 + (quarter & 1) * 32 + lane
+                                       : (args.mt0 + 2 * g + (int)rank) * kMTile + quarter * 32 + lane;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  args.dbg[(int64_t)(qrow - args.mt0 * kMTile) * NT + cb + i] = __uint_as_float(v[i]);
+              }
+            }
+            if (!live) return;
+            if (pe - cb > 32) { m = max32(v, m); return; }
+            int lo = pe - cb;
+            float m_next;
+            m = max32_split(v, m, lo, m_next);
+            finish_page(g, pp, m);
+            next_page();
+            if (!live) return;
+            if (pe - cb > 32) { m = m_next; return; }
+            while (true) {
+              const int rel = pe - cb;
+              const int hi = rel < 32 ? rel : 32;
+              m = max32_masked(v, m, lo, hi);
+              if (rel > 32) break;
+              finish_page(g, pp, m);
+              next_page();
+              if (!live) break;
+              lo = hi;
+              if (lo >= 32) break;
+            }
+          };
+
+          uint32_t v0[32], v1[32], v2[32], v3[32];
+          tmem_ld32(taddr, v0);
+          tmem_ld32(taddr + 32, v1);
+          if (!SPLIT) { tmem_ld32(taddr + 64, v2); tmem_ld32(taddr + 96, v3); }
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_u32(acc_empty_l + a * 8);    // accumulator back to the MMA warps
+          if (st_on) { st_wait += ec1 - ec0; st_hold += clock64() - ec1; }
+          if (live && (p < w0 || p >= w0 + kPW)) refill(p);
+          if (SPLIT || half == 1) skip_to(c_beg);
+          if (!DBG && (!live || pe > c_beg + NOWN * 32)) {
+            if (live) {
+              m = max32(v0, m);
+              m = max32(v1, m);
+              if (!SPLIT) { m = max32(v2, m); m = max32(v3, m); }
+            }
+          } else {
+            scan(v0, c_beg);
+            scan(v1, c_beg + 32);
+            if (!SPLIT) { scan(v2, c_beg + 64); scan(v3, c_beg + 96); }
+          }
+          if (SPLIT || half == 0) skip_to(NT);
+          rotate(m);
+          p_next = pp;
+          pend_next = ppend;
+        };
+
+#pragma unroll 1
+        for (int g = 0; g < NF; ++g) do_use(std::false_type{}, g);
+        if (ODD) do_use(std::true_type{}, NF);
+        p = p_next; pend = pend_next;
+      }
+      if (LIS_STATS_ON(args) && blockIdx.x < 2 && lane == 0) {
+        args.stats[rank * 64 + 4 + 2 * warp] = st_wait;     // epilogue warp: waiting for a full accumulator
+        args.stats[rank * 64 + 5 + 2 * warp] = st_hold;     //                wake -> release
+        if (warp == 0) args.stats[rank * 64 + 26] = clock64() - st_t0;
+      }
+      while (p < npages) {          // pages not closed by any tile: trailing empty pages (or ntiles == 0)
+        if (p < w0 || p >= w0 + kPW) refill(p);
+#pragma unroll 1
+        for (int g = 0; g < U; ++g) {
+          finish_page(g, p, rm[0]);
+          rotate(-INFINITY);
+        }
+        ++p;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();        // nobody leaves while the peer may still read its shared memory or signal its barriers
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace lis

@@ -1,0 +1,43 @@
+"""Cycle attribution inside cluster 0 of the CTA-pair kernel (needs the LIS_K1_STATS build: LIS_LIB=.../liblis_stats.so)."""
+import importlib, json, sys
+from pathlib import Path
+import torch
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+lis = importlib.import_module("multi-modal_colpali_b200")
+native = importlib.import_module("multi-modal_colpali_b200._native")
+scoring = importlib.import_module("multi-modal_colpali_b200.scoring")
+lib = native.load()
+dev = torch.device("cuda", 0)
+pages = 30_000
+idx = lis.LateInteractionIndex(pages * 1030, pages, device=dev)
+idx.fill_synthetic(pages, 1030, seed=7)
+store = idx._as_store()
+stats = torch.zeros(256, dtype=torch.int64, device=dev)
+for nq, qtok in [(8, 32), (12, 32), (32, 20), (24, 32)]:
+    q = torch.nn.functional.normalize(torch.randn(nq, qtok, 128, generator=torch.Generator().manual_seed(1)), dim=-1).to(torch.bfloat16).to(dev)
+    pq = scoring.pack_queries(q, dev)
+    scores = torch.empty((nq, pages), dtype=torch.float32, device=dev)
+    for name, tun in [("single", (0, 0, 0, 0, 1)), ("pair", (0, 0, 0, 0, 3))]:
+        native.check(lib.lis_set_tuning(*tun))
+        for _ in range(3):
+            scoring.maxsim_scores_device(pq, store, "f32", out=scores)
+        stats.zero_()
+        native.check(lib.lis_k1_stats(stats.data_ptr()))
+        scoring.maxsim_scores_device(pq, store, "f32", out=scores)
+        torch.cuda.synchronize()
+        native.check(lib.lis_k1_stats(None))
+        s = stats.tolist()
+        uses = max(s[3], 1)
+        rec = {"rows": nq * qtok, "mode": name, "uses_counted": s[3], "mma_loop_per_use": round(s[0] / uses),
+               "mma_wait_tiles_per_use": round(s[1] / uses), "mma_wait_acc_per_use": round(s[2] / uses),
+               "mma_issue_per_use": round(s[23] / uses),
+               "epi_wait_per_use": [round(s[4 + 2 * w] / uses) for w in range(8)],
+               "epi_hold_per_use": [round(s[5 + 2 * w] / uses) for w in range(8)]}
+        if name == "pair":
+            rec.update({"peer_epi_wait_per_use": [round(s[64 + 4 + 2 * w] / uses) for w in range(8)],
+                        "peer_epi_hold_per_use": [round(s[64 + 5 + 2 * w] / uses) for w in range(8)],
+                        "producer_wait_total": [s[24], s[64 + 24]], "producer_loop_total": [s[25], s[64 + 25]],
+                        "epi_loop_total": [s[26], s[64 + 26]], "mma_loop_total": s[0]})
+        print(json.dumps(rec), flush=True)
+lib.lis_set_tuning(0, 0, 0, 0, 0)

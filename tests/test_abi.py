@@ -46,7 +46,7 @@ def ref_plan(lens):
     segs, row = [], 0
     for q, n in enumerate(lens):
         while n > 0:
-            take = min(n, 128 - row % 128)
+            take = min(n, 64 - row % 64)     # cut at multiples of 64 packed rows (half an M tile)
             segs.append((q, row, row + take))
             row += take
             n -= take
@@ -62,8 +62,8 @@ def test_plan_queries(lis, lens):
     for t in range(tiles):
         inside = [s for s in range(plan.n_seg) if plan.seg_lo[s] // 128 == t]
         assert list(range(plan.mt_seg[t], plan.mt_seg[t + 1])) == inside
-    for s in range(plan.n_seg):      # a segment never straddles an M tile
-        assert plan.seg_lo[s] // 128 == (plan.seg_hi[s] - 1) // 128
+    for s in range(plan.n_seg):      # a segment never straddles half an M tile (hence never an M tile)
+        assert plan.seg_lo[s] // 64 == (plan.seg_hi[s] - 1) // 64
     for q in range(len(lens)):
         mine = list(range(plan.seg_first[q], plan.seg_first[q + 1]))
         assert sum(plan.seg_hi[s] - plan.seg_lo[s] for s in mine) == lens[q]

@@ -20,8 +20,9 @@ int main(void) {
   int32_t seg_query[8], seg_lo[8], seg_hi[8], mt_seg[8];
   int64_t n_mt = 0;
   int64_t n = lis_plan_queries(lens, 3, 8, seg_query, seg_lo, seg_hi, 8, mt_seg, &n_mt);
-  if (n != 3 || n_mt != 2) { printf("bad plan %lld %lld\n", (long long)n, (long long)n_mt); return 1; }
-  if (seg_lo[1] != 20 || seg_hi[1] != 128 || seg_lo[2] != 128 || seg_hi[2] != 170) return 2;
+  /* 20 | 150 cut at rows 64 and 128: [0,20) [20,64) [64,128) [128,170) */
+  if (n != 4 || n_mt != 2) { printf("bad plan %lld %lld\n", (long long)n, (long long)n_mt); return 1; }
+  if (seg_lo[1] != 20 || seg_hi[1] != 64 || seg_lo[2] != 64 || seg_hi[2] != 128 || seg_lo[3] != 128 || seg_hi[3] != 170) return 2;
   if (lis_abi_version() != LIS_ABI_VERSION) return 3;
   if (lis_set_tuning(100, 0, 0, 0, 0) != LIS_E_INVALID) return 4;
   if (strstr(lis_last_error(), "tile_n") == NULL) return 5;

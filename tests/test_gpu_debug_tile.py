@@ -42,3 +42,35 @@ def test_sim_tile_matches_matmul(lis, tile_n, a_in_tmem, dtype):
         }.items():
             print(name, (out - alt).abs().max().item())
     assert err.max() < 1e-3
+
+
+@pytest.mark.parametrize("n_mt", [3, 4])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_sim_pair_matches_matmul(lis, n_mt, dtype):
+    """CTA-pair form: M = 256 instructions (one query tile per CTA) and, for n_mt = 3, the final M = 128
+    instruction whose accumulator is laid out 64 rows x two column halves per CTA."""
+    from importlib import import_module
+
+    N = import_module("multi-modal_colpali_b200._native")
+    lib = N.load()
+    g = torch.Generator().manual_seed(11)
+    rows = n_mt * 128 - 28
+    q = torch.randn(rows, 128, generator=g).to(dtype).cuda()
+    p = torch.randn(256 + 40, 128, generator=g).to(dtype).cuda()
+    out = torch.full((n_mt * 128, 256), float("nan"), dtype=torch.float32, device="cuda")
+    rc = lib.lis_debug_sim_pair(q.data_ptr(), rows, p.data_ptr(), p.shape[0], 0 if dtype == torch.bfloat16 else 1,
+                                n_mt, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    N.check(rc)
+    torch.cuda.synchronize()
+    qf = torch.zeros(n_mt * 128, 128, device="cuda")
+    qf[:rows] = q.float()
+    ref = qf @ p[:256].float().T
+    err = (out - ref).abs()
+    if not (err.max() < 1e-3):
+        bad = (err > 1e-3) | err.isnan()
+        print("max err", err.max().item(), "bad fraction", bad.float().mean().item())
+        for t in range(n_mt):
+            blk = bad[t * 128:(t + 1) * 128]
+            print("tile", t, "bad rows", blk.any(1).nonzero().flatten()[:8].tolist(), "...", int(blk.any(1).sum()),
+                  "bad cols", blk.any(0).nonzero().flatten()[:8].tolist(), "...", int(blk.any(0).sum()))
+    assert err.max() < 1e-3

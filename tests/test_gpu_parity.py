@@ -192,6 +192,51 @@ def test_all_tilings_agree_bitwise(lis, oracle):
         lib.lis_set_tuning(0, 0, 0, 0, 0)
 
 
+@pytest.mark.parametrize("n_tiles", [2, 3, 4, 5, 6, 7, 9])
+def test_pair_kernel_every_tile_count(lis, oracle, n_tiles):
+    """CTA-pair form (cta_group::2): every pass shape -- M = 256 uses only (even tile counts) and a final
+    64/64-split M = 128 use (odd) -- against the oracle, and bit-identical to the single-CTA form."""
+    from importlib import import_module
+
+    N = import_module("multi-modal_colpali_b200._native")
+    lib = N.load()
+    g = torch.Generator().manual_seed(100 + n_tiles)
+    rows = n_tiles * 128 - 37                       # last tile partly filled
+    pattern = [20, 33, 7, 64, 1, 150, 90, 128, 45]   # queries straddling 64- and 128-row boundaries
+    q_lens, left, i = [], rows, 0
+    while left > 0:
+        n = min(pattern[i % len(pattern)], left)
+        q_lens.append(n); left -= n; i += 1
+    assert sum(q_lens) == rows
+    qs = ragged(g, q_lens)
+    p_lens = [int(x) for x in torch.randint(1, 700, (420,), generator=g)] + [0, 0, 1, 256, 512, 0, 31, 1030, 0]
+    ps = ragged(g, p_lens)
+    try:
+        for bs in (128, 16):
+            want = oracle.score_multi_vector_widened(qs, ps, batch_size=bs)
+            N.check(lib.lis_set_tuning(0, 0, 0, 0, 1))            # single CTA per SM (SS form)
+            single = lis.score_multi_vector(qs, ps, batch_size=bs, round_mode="f32")
+            single16 = lis.score_multi_vector(qs, ps, batch_size=bs)
+            for grp, ctas in ((7, 0), (4, 0), (0, 6), (0, 0)):
+                N.check(lib.lis_set_tuning(0, grp, ctas, 0, 3))   # CTA pairs
+                got = lis.score_multi_vector(qs, ps, batch_size=bs, round_mode="f32")
+                assert (got - want).abs().max().item() <= TOL_F32, (n_tiles, grp, ctas, bs)
+                assert torch.equal(got, single), (n_tiles, grp, ctas, bs)
+                got16 = lis.score_multi_vector(qs, ps, batch_size=bs)
+                assert torch.equal(got16, single16), (n_tiles, grp, ctas, bs)
+    finally:
+        lib.lis_set_tuning(0, 0, 0, 0, 0)
+
+
+def test_pair_kernel_fp16_and_uniform_pages(lis, oracle):
+    g = torch.Generator().manual_seed(21)
+    q = rand_unit(g, 32, 20, 128, dtype=torch.float16)           # 640 rows: 5 tiles, BASELINE configs[1] query shape
+    p = rand_unit(g, 333, 1030, 128, dtype=torch.float16)
+    want = oracle.score_multi_vector_widened(q, p)
+    got = lis.score_multi_vector(q, p, round_mode="f32")
+    assert (got - want).abs().max().item() <= TOL_F32
+
+
 # ---------------------------------------------------------------------------------------------
 def test_topk_matches_oracle_with_ties(lis, oracle):
     g = torch.Generator().manual_seed(9)
