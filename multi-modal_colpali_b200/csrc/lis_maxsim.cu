@@ -357,7 +357,7 @@ static int maxsim_impl(const void* q, const void* q_lo, int64_t q_rows, const in
     atm = false;
   }
   Maps m;   // single-CTA form: 128-row query box, nt-row page box
-  Maps mp;  // pair form: 64-row query box, 128-row page box
+  Maps mp;  // pair form: 64-row boxes for queries and pages
   bool have_single = false;
   auto single_maps = [&]() -> int {
     if (have_single) return LIS_OK;
@@ -383,7 +383,7 @@ static int maxsim_impl(const void* q, const void* q_lo, int64_t q_rows, const in
   if (pair) {
     rc = encode_rows_tmap(&mp.q, q, q_rows, 64, dtype);
     if (rc) return rc;
-    rc = encode_rows_tmap(&mp.p, tokens, n_rows, 128, dtype);
+    rc = encode_rows_tmap(&mp.p, tokens, n_rows, 64, dtype);
     if (rc) return rc;
   } else {
     rc = single_maps();
@@ -546,7 +546,7 @@ int lis_debug_sim_pair(const void* q, int64_t q_rows, const void* tokens, int64_
   CUtensorMap mq, mp;
   int rc = encode_rows_tmap(&mq, q, q_rows, 64, dtype);
   if (rc) return rc;
-  rc = encode_rows_tmap(&mp, tokens, n_rows, 128, dtype);
+  rc = encode_rows_tmap(&mp, tokens, n_rows, 64, dtype);
   if (rc) return rc;
   char* scratch = nullptr;
   LIS_CUDA_CHECK(cudaMalloc(&scratch, 256));

@@ -47,7 +47,7 @@ static int launch_pair(const CUtensorMap& q, const CUtensorMap& p, const MaxSimA
 }
 
 // n_mt query M tiles (2..7) in one pass: n_mt / 2 uses with M = 256 and, when n_mt is odd, one with M = 128.
-// q: tensor map of the packed query rows with a 64-row box; p: of the token store with a 128-row box.
+// q, p: tensor maps of the packed query rows and of the token store, both with 64-row boxes.
 int dispatch_maxsim_pair(const CUtensorMap& q, const CUtensorMap& p, const MaxSimArgs& a, int grid, cudaStream_t st,
                          bool dbg) {
   if (grid < 2 || (grid & 1)) {

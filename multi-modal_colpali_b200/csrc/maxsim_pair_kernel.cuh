@@ -4,16 +4,22 @@
 // 05_experiment02.py:214; einsum("bnd,csd->bcns").max(3).sum(2), HF processing_colpali.py:360), but
 // two SMs work on every 256-row page tile together:
 //
-//   * each CTA of the pair TMA-loads HALF of the page tile (128 rows, 32 KB) -- the pair reads the
-//     page store ONCE for up to 7 query M tiles (a single CTA can keep 3 resident), and the 32 KB
-//     stages leave room for a 3..6-deep TMA ring next to the resident queries;
-//   * one elected thread of the leader CTA issues tcgen05.mma.cta_group::2: D[256 x 256] = A[256 x 128] B^T,
-//     CTA r supplying query tile (2u + r) as its half of A and reading both halves of B.  Operand
-//     fetch drops from 96 to 64 B/clk per SM, so TMA writes no longer compete with the tensor pipe;
-//   * an ODD tile count ends with one M = 128 instruction per k-step: the last query tile is split
-//     64/64 rows over the pair, at full tensor rate (no padded tile).  Its accumulator sits in
-//     TMEM as lanes 0-63 = rows x columns [0,128), lanes 64-127 = the same rows x columns [128,256)
-//     (the "2x2" layout of cute's tmem_frg_2sm<M_MMA=64>).
+//   * each CTA of the pair TMA-loads HALF of the page tile (32 KB) -- the pair reads the page store ONCE
+//     for up to 7 query M tiles (a single CTA can keep 3 resident), and the 32 KB stages leave room
+//     for a 3..5-deep TMA ring next to the resident queries;
+//   * one elected thread of the leader CTA issues tcgen05.mma.cta_group::2.  The accumulators form a
+//     ring of FOUR 128-column TMEM slots, each filled by one "use" of 8 k-steps x 64 cycles:
+//       - a query-tile pair (one tile per CTA) against half h of the page tile: D[256 x 128] = A[256 x 128] B_h^T
+//         (each CTA supplies 64 of B_h's 128 rows: CTA r holds tile rows h*128 + r*64 .. +64);
+//       - for an ODD tile count, the last query tile split 64/64 rows over the pair against the whole
+//         page tile: D[128 x 256], which cute's "2x2" layout (tmem_frg_2sm<M_MMA=64>) also puts into 128
+//         columns: lanes 0-63 = rows x instruction columns [0,128), lanes 64-127 = rows x [128,256).
+//     Four slots matter: the round trip accumulator-free -> MMA issued -> MMAs done -> epilogue awake is
+//     ~1000+ cycles on top of the MMA time, so a ring of two 256-column slots caps the tensor pipe at
+//     ~83 % (measured); four 128-column slots cover it.
+//   * the eight epilogue warps form two sets of four (one warp per TMEM lane quarter); set s drains the
+//     uses of parity s, all 128 columns of a slot per warp.  The two warps of a scheduler are therefore
+//     always in different phases (one waits for tcgen05.ld while the other reduces).
 //
 // Each CTA owns the scores of ITS query rows for all pages of the pair's range, so every output
 // element still has exactly one writer.  Segments must not straddle the 64-row midpoint of a tile
@@ -77,25 +83,27 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       : "memory");
 }
 
-constexpr int kPairTail = 3072;   // bytes of barriers / tables behind the operand stages
+constexpr int kPairTail = 5120;   // bytes of barriers / tables / exchange slots behind the operand stages
 constexpr int kPairWindow = 64;   // page-table window (pages)
+constexpr int kPairEx = 4;        // exchange slots between the epilogue warps and the page reducer
 
-// NF: uses with M = 256 (two query tiles, one per CTA); ODD: a final use with M = 128 (one tile, 64 rows per CTA).
+// NF: query-tile pairs (M = 256 uses, one tile per CTA); ODD: a final tile split 64/64 over the pair (M = 128 use).
 template <int NF, bool ODD, bool DBG>
 __global__ void __launch_bounds__(kCtrlThreads + 256, 1)
 maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_p,
                    const MaxSimArgs args, const int NS) {
-  constexpr int NT = 256;                 // page rows per tile (N of the MMA)
-  constexpr int EH = 2;                   // two epilogue warps per TMEM lane quarter
-  constexpr int U = NF + (ODD ? 1 : 0);   // uses (accumulator hand-overs) per page tile
-  constexpr int NACC = 2;
-  constexpr int kAFull = kMTile * kDim * 2;        // 32 KB: this CTA's tile of an M = 256 use
+  constexpr int NT = 256;                 // page rows per tile
+  constexpr int U = NF + (ODD ? 1 : 0);   // query-tile groups per pass ("g")
+  constexpr int NACC = 4;                 // accumulator slots
+  constexpr int kSlotCols = 128;
+  constexpr int kAFull = kMTile * kDim * 2;        // 32 KB: this CTA's tile of a pair
   constexpr int kAHalfTile = 64 * kDim * 2;        // 16 KB: this CTA's 64 rows of the split tile
   constexpr int kABytes = NF * kAFull + (ODD ? kAHalfTile : 0);
-  constexpr int kBRows = NT / 2;                   // page rows of a tile held by this CTA
-  constexpr int kBStage = kBRows * kDim * 2;       // 32 KB
-  constexpr int kBHalf = kBRows * 128;             // one K half (64 elements) of the stage
+  constexpr int kBStage = (NT / 2) * kDim * 2;     // 32 KB: [K half][box h][64 rows x 128 B]
+  constexpr int kBKHalf = (NT / 2) * 128;          // 16 KB: one K half (64 elements) of the stage
+  constexpr int kBBox = 64 * 128;                  //  8 KB: the CTA's 64 rows of tile half h
   constexpr int kPW = kPairWindow;
+  constexpr int kEx = kPairEx;
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
@@ -104,26 +112,26 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint64_t* q_full = reinterpret_cast<uint64_t*>(tail);      // 1   (leader's is used)
   uint64_t* b_full = q_full + 1;                             // [8] (leader's are used)
   uint64_t* b_empty = b_full + 8;                            // [8] per CTA
-  uint64_t* acc_full = b_empty + 8;                          // [2] per CTA
-  uint64_t* acc_empty = acc_full + 2;                        // [2] (leader's are used; both CTAs' warps arrive)
-  uint64_t* ex_full = acc_empty + 2;                         // [2]
-  uint64_t* ex_empty = ex_full + 2;                          // [2]
-  int64_t* ex_meta = reinterpret_cast<int64_t*>(ex_empty + 2);   // [2][2]
-  int64_t* range = ex_meta + 4;                                  // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(range + 4);  // [2]
-  float* srm = reinterpret_cast<float*>(tmem_slot + 2);          // [2][256]
-  int32_t* pw_end = reinterpret_cast<int32_t*>(srm + 2 * EH * kMTile);   // [kPW]
-  int32_t* seginfo = pw_end + kPW;                                      // [U][2]
-  uint16_t* segtab = reinterpret_cast<uint16_t*>(seginfo + 2 * U);      // [U][16]
-  uint8_t* pw_clamp = reinterpret_cast<uint8_t*>(segtab + 16 * U);      // [kPW]
-  static_assert((1 + 8 + 8 + 2 + 2 + 2 + 2 + 4 + 4) * 8 + 8 + 2 * EH * kMTile * 4 + kPW * 4 + U * 8 + U * 32 + kPW <=
+  uint64_t* acc_full = b_empty + 8;                          // [4] per CTA
+  uint64_t* acc_empty = acc_full + NACC;                     // [4] (leader's are used; both CTAs' warps arrive)
+  uint64_t* ex_full = acc_empty + NACC;                      // [kEx]
+  uint64_t* ex_empty = ex_full + kEx;                        // [kEx]
+  int64_t* ex_meta = reinterpret_cast<int64_t*>(ex_empty + kEx);   // [kEx][2]
+  int64_t* range = ex_meta + 2 * kEx;                              // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(range + 4);    // [2]
+  float* srm = reinterpret_cast<float*>(tmem_slot + 2);            // [kEx][256]
+  int32_t* pw_end = reinterpret_cast<int32_t*>(srm + kEx * 2 * kMTile);   // [kPW]
+  int32_t* seginfo = pw_end + kPW;                                       // [U][2]
+  uint16_t* segtab = reinterpret_cast<uint16_t*>(seginfo + 2 * U);       // [U][16]
+  uint8_t* pw_clamp = reinterpret_cast<uint8_t*>(segtab + 16 * U);       // [kPW]
+  static_assert((1 + 8 + 8 + 2 * NACC + 2 * kEx + 2 * kEx + 4) * 8 + 8 + kEx * 2 * kMTile * 4 + kPW * 4 + U * 8 + U * 32 + kPW <=
                     kPairTail, "tail does not fit");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int kReducerWarp = 4 * EH;
-  constexpr int kProducerWarp = 4 * EH + 1;
-  constexpr int kMmaWarp = 4 * EH + 2;
+  constexpr int kReducerWarp = 8;
+  constexpr int kProducerWarp = 9;
+  constexpr int kMmaWarp = 10;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int mt_split = args.mt0 + 2 * NF;       // the tile shared 64/64 by the pair (ODD only)
@@ -133,8 +141,8 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     tma_prefetch_desc(&tmap_p);
     mbar_init(q_full, 1);
     for (int s = 0; s < NS; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, kMmaWarps); }
-    for (int a = 0; a < NACC; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, 2 * 4 * EH); }
-    for (int i = 0; i < 2; ++i) { mbar_init(ex_full + i, 4 * EH); mbar_init(ex_empty + i, 1); }
+    for (int a = 0; a < NACC; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, 2 * 4); }
+    for (int i = 0; i < kEx; ++i) { mbar_init(ex_full + i, 8); mbar_init(ex_empty + i, 1); }
     fence_barrier_init();
     // The PAIR's contiguous range of whole pages, balanced by token rows.
     const int64_t np = args.np;
@@ -201,18 +209,22 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         if (elect_one_sync()) {
           if (leader) mbar_arrive_expect_tx(b_full + s, 2u * kBStage);
           const uint32_t dst = b0 + (uint32_t)s * kBStage;
-          const int32_t r = (int32_t)(row0 + (int64_t)t * NT) + (int32_t)rank * kBRows;
-          tma_load_2d_pair(dst, &tmap_p, b_full_l + s * 8, 0, r, kPolicyEvictFirst);
-          tma_load_2d_pair(dst + kBHalf, &tmap_p, b_full_l + s * 8, kKHalf, r, kPolicyEvictFirst);
+          const int32_t r = (int32_t)(row0 + (int64_t)t * NT) + (int32_t)rank * 64;
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)    // this CTA's 64 rows of tile half h
+              tma_load_2d_pair(dst + kh * kBKHalf + h * kBBox, &tmap_p, b_full_l + s * 8, kh * kKHalf, r + h * 128,
+                               kPolicyEvictFirst);
         }
         __syncwarp();
       }
-      // tail: every release of a stage (a multicast commit issued by the leader) has landed here before
-      // this CTA may leave -- wait for the hand-back of the last tile that used each stage
       if (st_on && lane == 0) {
         args.stats[rank * 64 + 24] = st_wait;              // producer: waiting for a free stage
         args.stats[rank * 64 + 25] = clock64() - st_t0;    //           whole loop
       }
+      // tail: every release of a stage (a multicast commit issued by the leader) has landed here before
+      // this CTA may leave -- wait for the hand-back of the last tile that used each stage
       for (int t = ntiles; t < ntiles + NS; ++t)
         if (t >= NS) mbar_wait(b_empty + t % NS, ((uint32_t)(t / NS) & 1u) ^ 1u);
     }
@@ -220,8 +232,8 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     // ===================== MMA issuers (leader CTA only) =====================
     if (leader && pa < pb && ntiles > 0) {
       const uint32_t fmt = args.is_bf16 ? 1u : 0u;
-      const uint32_t idesc_full = make_idesc_f16(fmt, 256, NT);
-      const uint32_t idesc_split = make_idesc_f16(fmt, 128, NT);
+      const uint32_t idesc_full = make_idesc_f16(fmt, 256, 128);     // tile pair x half page tile
+      const uint32_t idesc_split = make_idesc_f16(fmt, 128, 256);    // split tile x whole page tile
       const uint32_t a_base = smem_u32(smem_a);
       const uint32_t b_base = smem_u32(smem_b);
       const uint32_t acc_full_u = smem_u32(acc_full), b_empty_u = smem_u32(b_empty);
@@ -239,32 +251,37 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         if (st_on) st_b += clock64() - c0;
         tc_fence_after();
         bool issued = false;
+        // one use: a_off / b_off = operand offsets of k-step 0; a_kh = bytes between the K halves of A
+        auto issue_use = [&](uint32_t a_off, uint32_t a_kh, uint32_t b_off, uint32_t idesc) {
+          if (use % kMmaWarps == my) {
+            issued = true;
+            const uint32_t slot = use & (NACC - 1);
+            const long long w0c = st_on ? clock64() : 0;
+            mbar_wait(acc_empty + slot, ((use / NACC) & 1u) ^ 1u);
+            const long long w1c = st_on ? clock64() : 0;
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + slot * kSlotCols;
+            if (LIS_ISSUE_PRED) {
 #pragma unroll
-        for (int u = 0; u < U; ++u, ++use) {
-          if (use % kMmaWarps != my) continue;
-          issued = true;
-          const uint32_t a = use & 1u;
-          c0 = st_on ? clock64() : 0;
-          mbar_wait(acc_empty + a, ((use >> 1) & 1u) ^ 1u);
-          const long long c1 = st_on ? clock64() : 0;
-          if (st_on) st_acc += c1 - c0;
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + a * NT;
-          const bool split = ODD && u == NF;
-          if (LIS_ISSUE_PRED) {
-#pragma unroll
-            for (int k = 0; k < kDim / 16; ++k) {
-              const uint32_t koff_a = (uint32_t)(k >> 2) * (split ? 8192u : (uint32_t)(kMTile * 128)) + (uint32_t)(k & 3) * 32;
-              const uint32_t koff_b = (uint32_t)(k >> 2) * kBHalf + (uint32_t)(k & 3) * 32;
-              const uint64_t adesc = make_kmajor_sw128_desc(a_base + u * kAFull + koff_a);
-              const uint64_t bdesc = make_kmajor_sw128_desc(b_base + s * kBStage + koff_b);
-              umma_f16_pair(d_tmem, adesc, bdesc, split ? idesc_split : idesc_full, k ? 1u : 0u);
+              for (int k = 0; k < kDim / 16; ++k) {
+                const uint64_t adesc = make_kmajor_sw128_desc(a_base + a_off + (uint32_t)(k >> 2) * a_kh + (uint32_t)(k & 3) * 32);
+                const uint64_t bdesc = make_kmajor_sw128_desc(b_base + s * kBStage + b_off + (uint32_t)(k >> 2) * kBKHalf +
+                                                              (uint32_t)(k & 3) * 32);
+                umma_f16_pair(d_tmem, adesc, bdesc, idesc, k ? 1u : 0u);
+              }
+              umma_commit_pair(acc_full_u + slot * 8);
             }
-            umma_commit_pair(acc_full_u + a * 8);
+            __syncwarp();
+            if (st_on) { st_acc += w1c - w0c; st_issue += clock64() - w1c; }
           }
-          __syncwarp();
-          if (st_on) st_issue += clock64() - c1;
+          ++use;
+        };
+#pragma unroll
+        for (int g = 0; g < NF; ++g) {
+          issue_use(g * kAFull, kMTile * 128, 0, idesc_full);
+          issue_use(g * kAFull, kMTile * 128, kBBox, idesc_full);
         }
+        if (ODD) issue_use(NF * kAFull, 8192, 0, idesc_split);
         // hand the page tile back to both producers once this warp's MMAs on it are done
         if (LIS_ISSUE_PRED) {
           if (issued) umma_commit_pair(b_empty_u + s * 8);
@@ -275,7 +292,7 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       if (st_on && lane == 0) {
         args.stats[0] = clock64() - st_t0;   // MMA warp 0: whole loop
         args.stats[1] = st_b;                //   waiting for page tiles
-        args.stats[2] = st_acc;              //   waiting for a free accumulator
+        args.stats[2] = st_acc;              //   waiting for a free accumulator slot
         args.stats[3] = use;
         args.stats[23] = st_issue;           //   issuing MMAs + commit
       }
@@ -288,17 +305,18 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const bool round_sum = round_ref && (args.round_mode & 2) == 0;
       const int64_t nfin = (pb - pa) * U;
       for (int64_t f = 0; f < nfin; ++f) {
-        const int slot = (int)(f & 1);
-        mbar_wait(ex_full + slot, (uint32_t)(f >> 1) & 1u);
+        const int slot = (int)(f % kEx);
+        mbar_wait(ex_full + slot, (uint32_t)(f / kEx) & 1u);
         const int64_t p = ex_meta[2 * slot];
         const int g = (int)(ex_meta[2 * slot + 1] & 0xff);
         const bool clamp = (ex_meta[2 * slot + 1] >> 8) != 0;
-        const float* ex = srm + slot * (EH * kMTile);
+        const float* ex = srm + slot * (2 * kMTile);
         const bool split = ODD && g == NF;
         const int mt = split ? mt_split : args.mt0 + 2 * g + (int)rank;
-        const int rbase = split ? (int)rank * 64 : 0;       // first tile row this CTA owns in this use
+        const int rbase = split ? (int)rank * 64 : 0;       // first tile row this CTA owns in this group
         const int rcnt = split ? 64 : kMTile;
         const int seg_first = seginfo[2 * g], seg_cnt = seginfo[2 * g + 1];
+        // partial maxima: [warp set][row] for a tile pair, [warp set][lane half][row] for the split tile
         reduce_tile_segments(ex, split ? 4 : 2, split ? 64 : kMTile, segtab + g * 16, args.seg_lo, args.seg_hi, seg_first,
                              seg_cnt, mt * kMTile, rbase, rcnt, clamp, round_ref, round_sum, is_bf16, args.out + p,
                              args.ld_out, lane);
@@ -308,13 +326,15 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
   } else {
     // ===================== epilogue (warps 0..7, both CTAs) =====================
-    // M = 256 use: thread = query row (lane quarter * 32 + lane) of this CTA's tile; the two warps of a lane
-    // quarter scan tile columns [0,128) and [128,256).  Split use: lanes 0-63 hold this CTA's 64 rows x
-    // columns [0,128), lanes 64-127 the same rows x columns [128,256), so a warp scans 64 columns and four
-    // partial maxima per row meet in the exchange slot.
+    // Warp = (TMEM lane quarter, set).  Set s drains the uses of parity s: all 128 columns of the slot,
+    // thread = accumulator lane.  A tile-pair use covers one half of the page tile (tile columns
+    // h*128 .. +128, thread = query row of this CTA's tile); the split use covers, per lane half L,
+    // instruction columns L*128 .. +128, which the row-to-CTA assignment of the page tile maps to tile
+    // columns [L*64, +64) and [128 + L*64, +64) (thread = one of this CTA's 64 rows).
     const int quarter = warp & 3;
-    const int half = warp >> 2;
-    const int etid = half * kMTile + quarter * 32 + lane;
+    const int set = warp >> 2;
+    const int lhalf = quarter >> 1;
+    const int etid = set * kMTile + quarter * 32 + lane;
     float rm[U];
 #pragma unroll
     for (int g = 0; g < U; ++g) rm[g] = -INFINITY;
@@ -325,13 +345,13 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     };
 
     const uint32_t acc_full_u = smem_u32(acc_full);
-    const uint32_t acc_empty_l = mapa_u32(smem_u32(acc_empty), 0);   // the leader's barrier, as a cluster address
+    const uint32_t acc_empty_l = mapa_u32(smem_u32(acc_empty), 0);   // the leader's barriers, as cluster addresses
     const uint32_t ex_full_u = smem_u32(ex_full), ex_empty_u = smem_u32(ex_empty);
     const int npages = (int)(pb - pa);
 
     int w0 = 0;
     auto refill = [&](int base) {
-      named_bar_sync(1, 128 * EH);
+      named_bar_sync(1, 256);
       if (etid < kPW) {
         const int pg = base + etid;
         int e = 0;
@@ -343,7 +363,7 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         pw_end[etid] = e;
         pw_clamp[etid] = c;
       }
-      named_bar_sync(1, 128 * EH);
+      named_bar_sync(1, 256);
       w0 = base;
     };
     if (etid < U * 16) {                       // segment tables of this CTA's tiles
@@ -356,11 +376,14 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                                         ((__ldg(args.seg_hi + first + j) - mt * kMTile) << 8));
     }
 
+    // Publish one finished page of group g: this thread's partial row maximum goes into the next exchange
+    // slot; the reducer takes over once all eight warps have arrived.  Nobody waits for anybody here
+    // unless the ring of kEx slots is full.
     uint32_t fin = 0;
     auto finish_page = [&](int g, int pi, float v) {
-      const uint32_t slot = fin & 1u;
-      mbar_wait_u32(ex_empty_u + slot * 8, ((fin >> 1) & 1u) ^ 1u);
-      srm[slot * (EH * kMTile) + etid] = v;
+      const uint32_t slot = fin % kEx;
+      mbar_wait_u32(ex_empty_u + slot * 8, ((fin / kEx) & 1u) ^ 1u);
+      srm[slot * (2 * kMTile) + etid] = v;
       if (etid == 0) {
         ex_meta[2 * slot] = pa + pi;
         ex_meta[2 * slot + 1] = (int64_t)g | ((int64_t)pw_clamp[pi - w0] << 8);
@@ -375,28 +398,19 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       int p = 0;
       refill(0);
       int pend = pw_end[0];
-      uint32_t use = 0;
+      uint32_t use_base = 0;                            // first use of the current (tile, group)
       const long long st_t0 = clock64();
       const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const bool st_on = LIS_STATS_ON(args) && blockIdx.x < 2;
       for (int t = 0; t < ntiles; ++t) {
         const int tcol = t * NT;
         auto rel_end = [&](int e) { const int d = e - tcol; return d > NT ? NT + 1 : d; };
         const int pe_tile = rel_end(pend);
         int p_next = p, pend_next = pend;
 
-        // one use: SPLIT selects the M = 128 accumulator layout
-        auto do_use = [&](auto split_tag, const int g) {
-          constexpr bool SPLIT = decltype(split_tag)::value;
-          constexpr int NOWN = SPLIT ? 2 : 4;                        // 32-column chunks scanned by this warp
-          const int c_beg = SPLIT ? (quarter >> 1) * 128 + half * 64 : half * 128;   // its first tile column
-          const uint32_t a = use & 1u;
-          const bool st_on = LIS_STATS_ON(args) && blockIdx.x < 2;
-          const long long ec0 = st_on ? clock64() : 0;
-          mbar_wait_u32(acc_full_u + a * 8, (use >> 1) & 1u);
-          const long long ec1 = st_on ? clock64() : 0;
-          tc_fence_after();
-          ++use;
-          const uint32_t taddr = tlane + a * NT + (SPLIT ? half * 64 : half * 128);
+        // One query-tile group against this page tile.  Every warp walks the pages that end inside the
+        // tile (it must publish its partial maxima for each of them); at most one use of the group is its own.
+        auto do_group = [&](const int g, const bool split) {
           int pp = p, ppend = pend;
           bool live = pp < npages;
           int pe = pe_tile;
@@ -410,13 +424,13 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             ppend = pw_end[pp - w0];
             pe = rel_end(ppend);
           };
-          auto skip_to = [&](int col_end) {
+          auto skip_to = [&](int col_end) {          // pages that end at or before tile column col_end
             while (live && pe <= col_end) { finish_page(g, pp, m); next_page(); }
           };
-          auto scan = [&](const uint32_t (&v)[32], int cb) {
+          auto scan = [&](const uint32_t (&v)[32], int cb) {      // one 32-column chunk starting at tile column cb
             if (DBG) {
               if (blockIdx.x < 2 && t == 0 && args.dbg != nullptr) {
-                const int qrow = SPLIT ? mt_split * kMTile + (int)rank * 64 + (quarter & 1) * 32 + lane
+                const int qrow = split ? mt_split * kMTile + (int)rank * 64 + (quarter & 1) * 32 + lane
                                        : (args.mt0 + 2 * g + (int)rank) * kMTile + quarter * 32 + lane;
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
@@ -445,41 +459,66 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             }
           };
 
-          uint32_t v0[32], v1[32], v2[32], v3[32];
-          tmem_ld32(taddr, v0);
-          tmem_ld32(taddr + 32, v1);
-          if (!SPLIT) { tmem_ld32(taddr + 64, v2); tmem_ld32(taddr + 96, v3); }
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster_u32(acc_empty_l + a * 8);    // accumulator back to the MMA warps
-          if (st_on) { st_wait += ec1 - ec0; st_hold += clock64() - ec1; }
-          if (live && (p < w0 || p >= w0 + kPW)) refill(p);
-          if (SPLIT || half == 1) skip_to(c_beg);
-          if (!DBG && (!live || pe > c_beg + NOWN * 32)) {
-            if (live) {
-              m = max32(v0, m);
-              m = max32(v1, m);
-              if (!SPLIT) { m = max32(v2, m); m = max32(v3, m); }
-            }
+          if (live && (p < w0 || p >= w0 + kPW)) refill(p);   // (rare) cursor rewound out of the window
+          // which use of this group, if any, belongs to this warp's set
+          uint32_t my_use = use_base;
+          int cb0, cb1;
+          bool have = true;
+          if (!split) {
+            const int h = ((use_base & 1u) == (uint32_t)set) ? 0 : 1;
+            my_use = use_base + h;
+            cb0 = h * 128; cb1 = cb0 + 64;
           } else {
-            scan(v0, c_beg);
-            scan(v1, c_beg + 32);
-            if (!SPLIT) { scan(v2, c_beg + 64); scan(v3, c_beg + 96); }
+            have = (use_base & 1u) == (uint32_t)set;
+            cb0 = lhalf * 64; cb1 = 128 + lhalf * 64;
           }
-          if (SPLIT || half == 0) skip_to(NT);
+          use_base += split ? 1u : 2u;
+          if (have) {
+            const uint32_t slot = my_use & (NACC - 1);
+            const long long ec0 = st_on ? clock64() : 0;
+            mbar_wait_u32(acc_full_u + slot * 8, (my_use / NACC) & 1u);
+            const long long ec1 = st_on ? clock64() : 0;
+            tc_fence_after();
+            const uint32_t taddr = tlane + slot * kSlotCols;
+            uint32_t v0[32], v1[32], v2[32], v3[32];
+            tmem_ld32(taddr, v0);
+            tmem_ld32(taddr + 32, v1);
+            tmem_ld32(taddr + 64, v2);
+            tmem_ld32(taddr + 96, v3);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_u32(acc_empty_l + slot * 8);    // slot back to the MMA warps
+            if (st_on) { st_wait += ec1 - ec0; st_hold += clock64() - ec1; }
+            skip_to(cb0);
+            if (!DBG && (!live || pe > cb1 + 64)) {
+              if (live) {                      // fast path: no page ends inside this warp's columns
+                m = max32(v0, m);
+                m = max32(v1, m);
+                m = max32(v2, m);
+                m = max32(v3, m);
+              }
+            } else {
+              scan(v0, cb0);
+              scan(v1, cb0 + 32);
+              skip_to(cb1);
+              scan(v2, cb1);
+              scan(v3, cb1 + 32);
+            }
+          }
+          skip_to(NT);
           rotate(m);
           p_next = pp;
           pend_next = ppend;
         };
 
 #pragma unroll 1
-        for (int g = 0; g < NF; ++g) do_use(std::false_type{}, g);
-        if (ODD) do_use(std::true_type{}, NF);
+        for (int g = 0; g < NF; ++g) do_group(g, false);
+        if (ODD) do_group(NF, true);
         p = p_next; pend = pend_next;
       }
       if (LIS_STATS_ON(args) && blockIdx.x < 2 && lane == 0) {
-        args.stats[rank * 64 + 4 + 2 * warp] = st_wait;     // epilogue warp: waiting for a full accumulator
+        args.stats[rank * 64 + 4 + 2 * warp] = st_wait;     // epilogue warp: waiting for a full accumulator slot
         args.stats[rank * 64 + 5 + 2 * warp] = st_hold;     //                wake -> release
         if (warp == 0) args.stats[rank * 64 + 26] = clock64() - st_t0;
       }
