@@ -100,6 +100,11 @@ int lis_maxsim_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, cons
                       int64_t n_rows, const int64_t* p_offsets, const uint8_t* p_clamp, int64_t np,
                       int dtype, int round_mode, float* out, int64_t ld_out, void* stream);
 
+/* How lis_maxsim_scores will cover n_mtiles query M tiles with the current tuning: one entry per pass over the
+ * page store, +n = n tiles resident on one CTA per SM, -n = n tiles on CTA pairs.  Returns the number of passes
+ * (writes at most `cap` entries; cap = 0 just counts).  Host-only; used by bench.py to state launches and bytes. */
+int lis_maxsim_pass_plan(int64_t n_mtiles, int32_t* passes, int cap);
+
 /* fp32 embeddings (ColFlor's default dtype, 05_experiment02.py:343-347) on the bf16 tensor pipe:
  * every operand is split into two bf16 planes, x = hi + lo, and a tile product is computed as
  * hi*hi + hi*lo + lo*hi in fp32 accumulators (error ~1e-6 on unit-norm rows).  lis_split_f32 produces
@@ -121,13 +126,13 @@ int lis_reduce_segments(const float* seg_scores, int64_t ld_seg, const int32_t* 
 
 /* Tuning / debug knobs (process-wide); 0 always means "auto", and the defaults are what ships.
  *   tile_n     {0, 128, 192, 256}  page-token rows per MMA tile
- *   group      {0, 1..7}           query M tiles resident per pass over the page store (6, 7: CTA pairs only)
+ *   group      {0, 1..6}           most query M tiles resident per pass over the page store (4..6: CTA pairs only)
  *   max_ctas   0 = one per SM
  *   epi_halves {0, 1, 2}           4 or 8 epilogue warps
  *   a_operand  {0, 1, 2, 3}        query operand of the MMA in shared memory (1) or tensor memory (2) on one
  *                                  CTA per SM, or 3 = CTA pairs (clusters of 2, tcgen05 cta_group::2: every page
- *                                  tile is loaded once per pair and shared by up to 7 query tiles).  Auto: pairs
- *                                  whenever a pass holds >= 2 query tiles, one CTA per SM for a single tile. */
+ *                                  tile is loaded once per pair and shared by up to 6 query tiles).  Auto: the cheapest
+ *                                  mix of passes by measured cost (one CTA per SM up to 3 tiles, pairs from 4). */
 int lis_set_tuning(int tile_n, int group, int max_ctas, int epi_halves, int a_operand);
 /* Timing experiments only (scores become invalid): 1 = K1's epilogue skips the TMEM read-out, 2 = it skips
  * the max arithmetic, 3 = the producer issues no TMA loads after the first ring fill (stale tiles are reused),

@@ -40,6 +40,7 @@ SIGNATURES = {
     "lis_plan_queries": (_i64, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp]),
     "lis_maxsim_scores": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32,
                                  _vp, _i64, _vp]),
+    "lis_maxsim_pass_plan": (_i32, [_i64, _vp, _i32]),
     "lis_split_f32": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "lis_maxsim_scores_f32x2": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i64,
                                        _vp, _i64, _vp]),

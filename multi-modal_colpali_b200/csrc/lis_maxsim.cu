@@ -187,9 +187,9 @@ int lis_set_tuning(int tile_n, int group, int max_ctas, int epi_halves, int a_op
               "a_operand must be 0 (auto), 1 (shared memory), 2 (tensor memory) or 3 (CTA pairs)");
   LIS_REQUIRE(epi_halves >= 0 && epi_halves <= 2, "epi_halves must be 0 (auto), 1 or 2");
   LIS_REQUIRE(max_ctas >= 0, "max_ctas must be >= 0");
-  LIS_REQUIRE(group >= 0 && group <= 7, "group must be in 0..7");
+  LIS_REQUIRE(group >= 0 && group <= 6, "group must be in 0..6");
   LIS_REQUIRE(a_operand == 3 || (a_operand == 0 && tile_n == 0) || group <= 5, "group > 5 needs the CTA-pair form");
-  LIS_REQUIRE(a_operand != 3 || group == 0 || group >= 2, "the CTA-pair form keeps 2..7 query tiles per pass");
+  LIS_REQUIRE(a_operand != 3 || group == 0 || group >= 2, "the CTA-pair form keeps 2..6 query tiles per pass");
   LIS_REQUIRE(a_operand != 3 || tile_n == 0 || tile_n == 256, "the CTA-pair form uses 256-row page tiles");
   if (tile_n && a_operand && a_operand != 3) {
     const int gm = max_group(tile_n, a_operand == 2);
@@ -321,6 +321,50 @@ static void choose_tiling(int64_t n_mtiles, int* nt, int* g, bool* atm) {
   *g = (int)((n_mtiles + passes - 1) / passes);
 }
 
+// Pass plan: which kernel form takes how many query tiles in each pass over the store.
+struct Pass { bool pair; int n; };
+static void build_pass_plan(int64_t n_mtiles, bool must_single, int g_single, std::vector<Pass>& plan) {
+  plan.clear();
+  const bool forced_single = must_single || g_tuning.a_operand == 1 || g_tuning.a_operand == 2 ||
+                             g_tuning.tile_n != 0 || g_tuning.group == 1;
+  const int g = g_single;
+  if (forced_single) {
+    for (int64_t t = 0; t < n_mtiles; t += g) plan.push_back({false, (int)std::min<int64_t>(g, n_mtiles - t)});
+  } else if (g_tuning.a_operand == 3) {
+    // experiments: CTA pairs only, balanced passes of at most `group` tiles (a leftover single tile runs on one CTA)
+    const int gmax = g_tuning.group ? std::min(std::max(g_tuning.group, 2), 6) : 6;
+    const int64_t passes = (n_mtiles + gmax - 1) / gmax;
+    const int gp = (int)((n_mtiles + passes - 1) / passes);
+    for (int64_t t = 0; t < n_mtiles; t += gp) {
+      const int n = (int)std::min<int64_t>(gp, n_mtiles - t);
+      plan.push_back({n >= 2, n});
+    }
+  } else {
+    // auto: the cheapest decomposition of n_mtiles by the measured steady-state cost of one pass of each
+    // form (ms per 60 000 ColPali pages on a power-capped B200, scripts/gpu_pass_costs.py -> profiles/).
+    // One CTA per SM wins up to 3 tiles (a single tile is HBM-bound); CTA pairs win from 4 tiles on,
+    // even tile counts being the efficient ones (no split tile).
+    static const float cost_single[4] = {0.f, 2.45f, 3.75f, 5.09f};
+    static const float cost_pair[7] = {0.f, 0.f, 3.83f, 5.59f, 6.38f, 8.54f, 9.00f};
+    const int gcap = g_tuning.group ? g_tuning.group : 6;     // group = most tiles a pass may hold
+    std::vector<float> best((size_t)n_mtiles + 1, 1e30f);
+    std::vector<int8_t> choice((size_t)n_mtiles + 1, 0);       // +n = single pass of n tiles, -n = pair pass
+    best[0] = 0.f;
+    for (int64_t t = 1; t <= n_mtiles; ++t) {
+      for (int n = 1; n <= 3 && n <= t && n <= gcap; ++n)
+        if (best[t - n] + cost_single[n] < best[t]) { best[t] = best[t - n] + cost_single[n]; choice[t] = (int8_t)n; }
+      for (int n = 2; n <= 6 && n <= t && n <= gcap; ++n)
+        if (best[t - n] + cost_pair[n] < best[t]) { best[t] = best[t - n] + cost_pair[n]; choice[t] = (int8_t)-n; }
+    }
+    for (int64_t t = n_mtiles; t > 0;) {
+      const int c = choice[t];
+      plan.push_back({c < 0, c < 0 ? -c : c});
+      t -= c < 0 ? -c : c;
+    }
+    std::sort(plan.begin(), plan.end(), [](const Pass& a, const Pass& b) { return a.pair != b.pair ? a.pair : a.n > b.n; });
+  }
+}
+
 static int maxsim_impl(const void* q, const void* q_lo, int64_t q_rows, const int32_t* seg_lo, const int32_t* seg_hi,
                        const int32_t* mt_seg, int64_t n_seg, int64_t n_mtiles, const void* tokens,
                        const void* tokens_lo, int64_t n_rows, const int64_t* p_offsets, const uint8_t* p_clamp,
@@ -345,17 +389,11 @@ static int maxsim_impl(const void* q, const void* q_lo, int64_t q_rows, const in
   bool atm;
   if (planes == 2) { nt = 128; g = 1; atm = false; }
   else choose_tiling(n_mtiles, &nt, &g, &atm);
-  // CTA pairs (cta_group::2) whenever two or more query tiles share a pass over the store: the pair reads
-  // every page tile once for up to 7 query tiles.  A single tile is HBM-bound and stays on one CTA per SM.
-  const bool want_pair = g_tuning.a_operand == 3 || (g_tuning.a_operand == 0 && g_tuning.tile_n == 0);
-  const bool pair = planes == 1 && want_pair && n_mtiles >= 2 && n_rows > 0 && g_tuning.group != 1 && sms >= 2;
-  if (pair) {
-    const int gmax = g_tuning.group ? std::min(std::max(g_tuning.group, 2), 7) : 6;
-    const int64_t passes = (n_mtiles + gmax - 1) / gmax;
-    g = (int)((n_mtiles + passes - 1) / passes);
-    nt = 256;
-    atm = false;
-  }
+  std::vector<Pass> plan;
+  build_pass_plan(n_mtiles, planes == 2 || n_rows == 0 || sms < 2, g, plan);
+  if (planes != 2 && !(g_tuning.a_operand == 1 || g_tuning.a_operand == 2 || g_tuning.tile_n != 0)) { nt = 256; atm = false; }
+  bool pair = false;
+  for (const Pass& ps : plan) pair = pair || ps.pair;
   Maps m;   // single-CTA form: 128-row query box, nt-row page box
   Maps mp;  // pair form: 64-row boxes for queries and pages
   bool have_single = false;
@@ -385,9 +423,6 @@ static int maxsim_impl(const void* q, const void* q_lo, int64_t q_rows, const in
     if (rc) return rc;
     rc = encode_rows_tmap(&mp.p, tokens, n_rows, 64, dtype);
     if (rc) return rc;
-  } else {
-    rc = single_maps();
-    if (rc) return rc;
   }
 
   int grid = sms;
@@ -397,7 +432,8 @@ static int maxsim_impl(const void* q, const void* q_lo, int64_t q_rows, const in
   if (g_tuning.max_ctas > 0) grid_pair = std::max(2, std::min(grid_pair, g_tuning.max_ctas & ~1));
   grid_pair = (int)std::min<int64_t>(grid_pair, 2 * std::max<int64_t>(np, 1));
 
-  for (int64_t mt0 = 0; mt0 < n_mtiles; mt0 += g) {
+  int64_t mt0 = 0;
+  for (const Pass& ps : plan) {
     MaxSimArgs a;
     a.p_offsets = p_offsets;
     a.p_clamp = p_clamp;
@@ -411,22 +447,34 @@ static int maxsim_impl(const void* q, const void* q_lo, int64_t q_rows, const in
     a.ld_out = ld_out;
     a.np = np;
     a.mt0 = (int32_t)mt0;
-    a.n_mt = (int32_t)std::min<int64_t>(g, n_mtiles - mt0);
+    a.n_mt = ps.n;
     a.round_mode = round_mode;
     a.is_bf16 = dtype == LIS_BF16;
     a.ablate = g_tuning.ablate;
     a.stats = g_stats;
-    if (pair && a.n_mt >= 2) {
+    if (ps.pair) {
       rc = dispatch_maxsim_pair(mp.q, mp.p, a, grid_pair, st, false);
     } else {
-      // the instantiation whose group equals this pass's tile count (the last pass may be short)
+      // the instantiation whose group equals this pass's tile count
       rc = single_maps();
       if (rc) return rc;
       rc = dispatch_maxsim(nt, a.n_mt, atm, m, a, grid, st, false, planes);
     }
     if (rc) return rc;
+    mt0 += ps.n;
   }
   return LIS_OK;
+}
+
+int lis_maxsim_pass_plan(int64_t n_mtiles, int32_t* passes, int cap) {
+  LIS_REQUIRE(n_mtiles > 0 && (cap == 0 || passes), "lis_maxsim_pass_plan: bad arguments");
+  int nt, g;
+  bool atm;
+  choose_tiling(n_mtiles, &nt, &g, &atm);
+  std::vector<Pass> plan;
+  build_pass_plan(n_mtiles, false, g, plan);
+  for (size_t i = 0; i < plan.size() && (int)i < cap; ++i) passes[i] = plan[i].pair ? -plan[i].n : plan[i].n;
+  return (int)plan.size();
 }
 
 int lis_maxsim_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, const int32_t* seg_hi,
