@@ -126,12 +126,12 @@ int lis_reduce_segments(const float* seg_scores, int64_t ld_seg, const int32_t* 
 
 /* Tuning / debug knobs (process-wide); 0 always means "auto", and the defaults are what ships.
  *   tile_n     {0, 128, 192, 256}  page-token rows per MMA tile
- *   group      {0, 1..6}           most query M tiles resident per pass over the page store (4..6: CTA pairs only)
+ *   group      {0, 1..10}          most query M tiles resident per pass over the page store (4..6, 8, 10: CTA pairs only)
  *   max_ctas   0 = one per SM
  *   epi_halves {0, 1, 2}           4 or 8 epilogue warps
  *   a_operand  {0, 1, 2, 3}        query operand of the MMA in shared memory (1) or tensor memory (2) on one
  *                                  CTA per SM, or 3 = CTA pairs (clusters of 2, tcgen05 cta_group::2: every page
- *                                  tile is loaded once per pair and shared by up to 6 query tiles).  Auto: the cheapest
+ *                                  tile is loaded once per pair and shared by up to 10 query tiles).  Auto: the cheapest
  *                                  mix of passes by measured cost (one CTA per SM up to 3 tiles, pairs from 4). */
 int lis_set_tuning(int tile_n, int group, int max_ctas, int epi_halves, int a_operand);
 /* Timing experiments only (scores become invalid): 1 = K1's epilogue skips the TMEM read-out, 2 = it skips

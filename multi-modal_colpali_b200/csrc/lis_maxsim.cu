@@ -187,9 +187,9 @@ int lis_set_tuning(int tile_n, int group, int max_ctas, int epi_halves, int a_op
               "a_operand must be 0 (auto), 1 (shared memory), 2 (tensor memory) or 3 (CTA pairs)");
   LIS_REQUIRE(epi_halves >= 0 && epi_halves <= 2, "epi_halves must be 0 (auto), 1 or 2");
   LIS_REQUIRE(max_ctas >= 0, "max_ctas must be >= 0");
-  LIS_REQUIRE(group >= 0 && group <= 6, "group must be in 0..6");
+  LIS_REQUIRE(group >= 0 && group <= 10, "group must be in 0..10");
   LIS_REQUIRE(a_operand == 3 || (a_operand == 0 && tile_n == 0) || group <= 5, "group > 5 needs the CTA-pair form");
-  LIS_REQUIRE(a_operand != 3 || group == 0 || group >= 2, "the CTA-pair form keeps 2..6 query tiles per pass");
+  LIS_REQUIRE(a_operand != 3 || group == 0 || group >= 2, "the CTA-pair form keeps 2..6, 8 or 10 query tiles per pass");
   LIS_REQUIRE(a_operand != 3 || tile_n == 0 || tile_n == 256, "the CTA-pair form uses 256-row page tiles");
   if (tile_n && a_operand && a_operand != 3) {
     const int gm = max_group(tile_n, a_operand == 2);
@@ -332,29 +332,35 @@ static void build_pass_plan(int64_t n_mtiles, bool must_single, int g_single, st
     for (int64_t t = 0; t < n_mtiles; t += g) plan.push_back({false, (int)std::min<int64_t>(g, n_mtiles - t)});
   } else if (g_tuning.a_operand == 3) {
     // experiments: CTA pairs only, balanced passes of at most `group` tiles (a leftover single tile runs on one CTA)
-    const int gmax = g_tuning.group ? std::min(std::max(g_tuning.group, 2), 6) : 6;
+    const int gmax = g_tuning.group ? std::min(std::max(g_tuning.group, 2), 10) : 6;
     const int64_t passes = (n_mtiles + gmax - 1) / gmax;
-    const int gp = (int)((n_mtiles + passes - 1) / passes);
+    int gp = (int)((n_mtiles + passes - 1) / passes);
+    if (gp == 7 || gp == 9) ++gp;                       // 7 and 9 resident tiles are not instantiated
     for (int64_t t = 0; t < n_mtiles; t += gp) {
-      const int n = (int)std::min<int64_t>(gp, n_mtiles - t);
+      int n = (int)std::min<int64_t>(gp, n_mtiles - t);
+      if (n == 7 || n == 9) {                           // leftover of 7 / 9: 6 + 1 / 6 + 3
+        plan.push_back({true, 6});
+        t += 6 - gp;                                    // (the loop adds gp)
+        continue;
+      }
       plan.push_back({n >= 2, n});
     }
   } else {
     // auto: the cheapest decomposition of n_mtiles by the measured steady-state cost of one pass of each
     // form (ms per 60 000 ColPali pages on a power-capped B200, scripts/gpu_pass_costs.py -> profiles/).
     // One CTA per SM wins up to 3 tiles (a single tile is HBM-bound); CTA pairs win from 4 tiles on,
-    // even tile counts being the efficient ones (no split tile).
-    static const float cost_single[4] = {0.f, 2.45f, 3.75f, 5.09f};
-    static const float cost_pair[7] = {0.f, 0.f, 3.83f, 5.59f, 6.38f, 8.54f, 9.00f};
-    const int gcap = g_tuning.group ? g_tuning.group : 6;     // group = most tiles a pass may hold
+    // even tile counts being the efficient ones (no split tile); 8 and 10 tiles amortise the page stream a little more.
+    static const float cost_single[4] = {0.f, 2.65f, 4.00f, 5.28f};
+    static const float cost_pair[11] = {0.f, 0.f, 4.05f, 5.73f, 6.58f, 8.83f, 9.30f, 0.f, 12.33f, 0.f, 15.20f};   // 0 = not instantiated
+    const int gcap = g_tuning.group ? g_tuning.group : 10;    // group = most tiles a pass may hold
     std::vector<float> best((size_t)n_mtiles + 1, 1e30f);
     std::vector<int8_t> choice((size_t)n_mtiles + 1, 0);       // +n = single pass of n tiles, -n = pair pass
     best[0] = 0.f;
     for (int64_t t = 1; t <= n_mtiles; ++t) {
       for (int n = 1; n <= 3 && n <= t && n <= gcap; ++n)
         if (best[t - n] + cost_single[n] < best[t]) { best[t] = best[t - n] + cost_single[n]; choice[t] = (int8_t)n; }
-      for (int n = 2; n <= 6 && n <= t && n <= gcap; ++n)
-        if (best[t - n] + cost_pair[n] < best[t]) { best[t] = best[t - n] + cost_pair[n]; choice[t] = (int8_t)-n; }
+      for (int n = 2; n <= 10 && n <= t && n <= gcap; ++n)
+        if (cost_pair[n] > 0.f && best[t - n] + cost_pair[n] < best[t]) { best[t] = best[t - n] + cost_pair[n]; choice[t] = (int8_t)-n; }
     }
     for (int64_t t = n_mtiles; t > 0;) {
       const int c = choice[t];

@@ -83,9 +83,11 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       : "memory");
 }
 
-constexpr int kPairTail = 5120;   // bytes of barriers / tables / exchange slots behind the operand stages
 constexpr int kPairWindow = 64;   // page-table window (pages)
-constexpr int kPairEx = 4;        // exchange slots between the epilogue warps and the page reducer
+// exchange slots between the epilogue warps and the page reducer, and the bytes of barriers / tables / exchange
+// slots behind the operand stages: 8 and 10 resident query tiles leave exactly 3 KB next to 3 / 2 page stages
+__host__ __device__ constexpr int pair_ex_slots(int nf) { return nf >= 4 ? 2 : 4; }
+__host__ __device__ constexpr int pair_tail_bytes(int nf) { return nf >= 4 ? 3072 : 5120; }
 
 // NF: query-tile pairs (M = 256 uses, one tile per CTA); ODD: a final tile split 64/64 over the pair (M = 128 use).
 template <int NF, bool ODD, bool DBG>
@@ -103,7 +105,8 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   constexpr int kBKHalf = (NT / 2) * 128;          // 16 KB: one K half (64 elements) of the stage
   constexpr int kBBox = 64 * 128;                  //  8 KB: the CTA's 64 rows of tile half h
   constexpr int kPW = kPairWindow;
-  constexpr int kEx = kPairEx;
+  constexpr int kEx = pair_ex_slots(NF);
+  constexpr int kPairTail = pair_tail_bytes(NF);
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
@@ -393,7 +396,7 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       ++fin;
     };
 
-    long long st_wait = 0, st_hold = 0;
+    long long st_wait = 0, st_hold = 0, st_hold_split = 0, st_wait_split = 0, st_n_split = 0;
     if (pa < pb) {
       int p = 0;
       refill(0);
@@ -489,7 +492,7 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster_u32(acc_empty_l + slot * 8);    // slot back to the MMA warps
-            if (st_on) { st_wait += ec1 - ec0; st_hold += clock64() - ec1; }
+            if (st_on) { st_wait += ec1 - ec0; const long long hc = clock64() - ec1; st_hold += hc; if (split) { st_hold_split += hc; st_wait_split += ec1 - ec0; ++st_n_split; } }
             skip_to(cb0);
             if (!DBG && (!live || pe > cb1 + 64)) {
               if (live) {                      // fast path: no page ends inside this warp's columns
@@ -521,6 +524,7 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         args.stats[rank * 64 + 4 + 2 * warp] = st_wait;     // epilogue warp: waiting for a full accumulator slot
         args.stats[rank * 64 + 5 + 2 * warp] = st_hold;     //                wake -> release
         if (warp == 0) args.stats[rank * 64 + 26] = clock64() - st_t0;
+        if (warp == 0 || warp == 4) { args.stats[rank * 64 + 28 + warp] = st_hold_split; args.stats[rank * 64 + 29 + warp] = st_n_split; args.stats[rank * 64 + 30 + warp] = st_wait_split; }
       }
       while (p < npages) {          // pages not closed by any tile: trailing empty pages (or ntiles == 0)
         if (p < w0 || p >= w0 + kPW) refill(p);

@@ -38,6 +38,10 @@ for nq, qtok in [(8, 32), (12, 32), (32, 20), (24, 32)]:
             rec.update({"peer_epi_wait_per_use": [round(s[64 + 4 + 2 * w] / uses) for w in range(8)],
                         "peer_epi_hold_per_use": [round(s[64 + 5 + 2 * w] / uses) for w in range(8)],
                         "producer_wait_total": [s[24], s[64 + 24]], "producer_loop_total": [s[25], s[64 + 25]],
-                        "epi_loop_total": [s[26], s[64 + 26]], "mma_loop_total": s[0]})
+                        "epi_loop_total": [s[26], s[64 + 26]], "mma_loop_total": s[0],
+                        "split_use_hold_wait_n_w0": [s[28] / max(s[29], 1), s[30] / max(s[29], 1), s[29]],
+                        "split_use_hold_wait_n_w4": [s[32] / max(s[33], 1), s[34] / max(s[33], 1), s[33]],
+                        "all_use_hold_w0_w4_per_own_use": [2 * s[5] / uses, 2 * s[5 + 8] / uses],
+                        "all_use_wait_w0_w4_per_own_use": [2 * s[4] / uses, 2 * s[4 + 8] / uses]})
         print(json.dumps(rec), flush=True)
 lib.lis_set_tuning(0, 0, 0, 0, 0)

@@ -192,7 +192,7 @@ def test_all_tilings_agree_bitwise(lis, oracle):
         lib.lis_set_tuning(0, 0, 0, 0, 0)
 
 
-@pytest.mark.parametrize("n_tiles", [2, 3, 4, 5, 6, 7, 9, 13])
+@pytest.mark.parametrize("n_tiles", [2, 3, 4, 5, 6, 7, 8, 9, 10, 13])
 def test_pair_kernel_every_tile_count(lis, oracle, n_tiles):
     """CTA-pair form (cta_group::2): every pass shape -- M = 256 uses only (even tile counts) and a final
     64/64-split M = 128 use (odd) -- against the oracle, and bit-identical to the single-CTA form."""
@@ -217,7 +217,7 @@ def test_pair_kernel_every_tile_count(lis, oracle, n_tiles):
             N.check(lib.lis_set_tuning(0, 0, 0, 0, 1))            # single CTA per SM (SS form)
             single = lis.score_multi_vector(qs, ps, batch_size=bs, round_mode="f32")
             single16 = lis.score_multi_vector(qs, ps, batch_size=bs)
-            for grp, ctas in ((6, 0), (4, 0), (3, 0), (0, 6), (0, 0)):
+            for grp, ctas in ((10, 0), (8, 0), (6, 0), (4, 0), (3, 0), (0, 6), (0, 0)):
                 N.check(lib.lis_set_tuning(0, grp, ctas, 0, 3))   # CTA pairs
                 got = lis.score_multi_vector(qs, ps, batch_size=bs, round_mode="f32")
                 assert (got - want).abs().max().item() <= TOL_F32, (n_tiles, grp, ctas, bs)
