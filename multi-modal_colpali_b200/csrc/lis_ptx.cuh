@@ -68,6 +68,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #endif
   return ok != 0;
 }
+// After a wait timed out: abort the launch.  -DLIS_WAIT_DIAG (debug builds) lingers ~0.3 s first so that every
+// other stuck waiter gets to print its barrier as well.
+__device__ __forceinline__ void lis_timeout_trap() {
+#ifdef LIS_WAIT_DIAG
+  const long long t0 = clock64();
+  while (clock64() - t0 < 600000000LL) {}
+#endif
+  __trap();
+}
 // Bounded wait: a pipeline bug must surface as a launch failure, never as a hung GPU.
 // ~4e9 SM cycles is about 2 s at boost clock; every legitimate wait is microseconds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -78,7 +87,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
       printf("lis: mbarrier wait timed out (block %d thread %d bar smem 0x%x parity %u)\n", blockIdx.x,
              threadIdx.x, smem_u32(bar), parity);
-      __trap();
+      lis_timeout_trap();
     }
   }
 }
@@ -106,7 +115,7 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
     if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
       printf("lis: mbarrier wait timed out (block %d thread %d bar smem 0x%x parity %u)\n", blockIdx.x, threadIdx.x,
              bar, parity);
-      __trap();
+      lis_timeout_trap();
     }
   }
 }

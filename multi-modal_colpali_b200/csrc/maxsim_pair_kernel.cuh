@@ -11,15 +11,19 @@
 //     ring of FOUR 128-column TMEM slots, each filled by one "use" of 8 k-steps x 64 cycles:
 //       - a query-tile pair (one tile per CTA) against half h of the page tile: D[256 x 128] = A[256 x 128] B_h^T
 //         (each CTA supplies 64 of B_h's 128 rows: CTA r holds tile rows h*128 + r*64 .. +64);
-//       - for an ODD tile count, the last query tile split 64/64 rows over the pair against the whole
-//         page tile: D[128 x 256], which cute's "2x2" layout (tmem_frg_2sm<M_MMA=64>) also puts into 128
-//         columns: lanes 0-63 = rows x instruction columns [0,128), lanes 64-127 = rows x [128,256).
+//       - for an ODD tile count, the last query tile split 64/64 rows over the pair, again against half h
+//         of the page tile: D[128 x 128] in 8 x 32 cycles, which cute's "2x2" layout (tmem_frg_2sm<M_MMA=64>)
+//         puts into 64 columns: lanes 0-63 = rows x columns [0,64), lanes 64-127 = rows x [64,128).
+//     Uses alternate between the two halves of the page tile, so use parity = half = issuing warp = draining
+//     warp set, and a slot (use & 3) always meets the same set: consecutive phases of its barriers are waited
+//     for by the same warps, which is what makes parity-only mbarrier waits unambiguous.
 //     Four slots matter: the round trip accumulator-free -> MMA issued -> MMAs done -> epilogue awake is
 //     ~1000+ cycles on top of the MMA time, so a ring of two 256-column slots caps the tensor pipe at
 //     ~83 % (measured); four 128-column slots cover it.
 //   * the eight epilogue warps form two sets of four (one warp per TMEM lane quarter); set s drains the
-//     uses of parity s, all 128 columns of a slot per warp.  The two warps of a scheduler are therefore
-//     always in different phases (one waits for tcgen05.ld while the other reduces).
+//     uses of page-tile half s, all columns of the slot per warp.  The two warps of a scheduler are therefore
+//     in different phases most of the time (one waits for tcgen05.ld while the other reduces), and both sets
+//     drain the same amount per page tile.
 //
 // Each CTA owns the scores of ITS query rows for all pages of the pair's range, so every output
 // element still has exactly one writer.  Segments must not straddle the 64-row midpoint of a tile
@@ -236,7 +240,7 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     if (leader && pa < pb && ntiles > 0) {
       const uint32_t fmt = args.is_bf16 ? 1u : 0u;
       const uint32_t idesc_full = make_idesc_f16(fmt, 256, 128);     // tile pair x half page tile
-      const uint32_t idesc_split = make_idesc_f16(fmt, 128, 256);    // split tile x whole page tile
+      const uint32_t idesc_split = make_idesc_f16(fmt, 128, 128);    // split tile (64 rows per CTA) x half page tile
       const uint32_t a_base = smem_u32(smem_a);
       const uint32_t b_base = smem_u32(smem_b);
       const uint32_t acc_full_u = smem_u32(acc_full), b_empty_u = smem_u32(b_empty);
@@ -281,10 +285,13 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         };
 #pragma unroll
         for (int g = 0; g < NF; ++g) {
-          issue_use(g * kAFull, kMTile * 128, 0, idesc_full);
-          issue_use(g * kAFull, kMTile * 128, kBBox, idesc_full);
+          issue_use(g * kAFull, kMTile * 128, 0, idesc_full);         // page-tile half 0 (even use: issuer 0, set 0)
+          issue_use(g * kAFull, kMTile * 128, kBBox, idesc_full);     // half 1
         }
-        if (ODD) issue_use(NF * kAFull, 8192, 0, idesc_split);
+        if (ODD) {                                                    // split tile: two short uses (8 x 32 cycles)
+          issue_use(NF * kAFull, 8192, 0, idesc_split);
+          issue_use(NF * kAFull, 8192, kBBox, idesc_split);
+        }
         // hand the page tile back to both producers once this warp's MMAs on it are done
         if (LIS_ISSUE_PRED) {
           if (issued) umma_commit_pair(b_empty_u + s * 8);
@@ -329,11 +336,9 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
   } else {
     // ===================== epilogue (warps 0..7, both CTAs) =====================
-    // Warp = (TMEM lane quarter, set).  Set s drains the uses of parity s: all 128 columns of the slot,
-    // thread = accumulator lane.  A tile-pair use covers one half of the page tile (tile columns
-    // h*128 .. +128, thread = query row of this CTA's tile); the split use covers, per lane half L,
-    // instruction columns L*128 .. +128, which the row-to-CTA assignment of the page tile maps to tile
-    // columns [L*64, +64) and [128 + L*64, +64) (thread = one of this CTA's 64 rows).
+    // Warp = (TMEM lane quarter, set); thread = accumulator lane.  A use covers half h of the page tile and
+    // belongs to set h: tile columns h*128 .. +128 with thread = query row of this CTA's tile (tile pair), or
+    // tile columns h*128 + L*64 .. +64 for lane half L with thread = one of this CTA's 64 rows (split tile).
     const int quarter = warp & 3;
     const int set = warp >> 2;
     const int lhalf = quarter >> 1;
@@ -463,20 +468,14 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           };
 
           if (live && (p < w0 || p >= w0 + kPW)) refill(p);   // (rare) cursor rewound out of the window
-          // which use of this group, if any, belongs to this warp's set
-          uint32_t my_use = use_base;
-          int cb0, cb1;
-          bool have = true;
-          if (!split) {
-            const int h = ((use_base & 1u) == (uint32_t)set) ? 0 : 1;
-            my_use = use_base + h;
-            cb0 = h * 128; cb1 = cb0 + 64;
-          } else {
-            have = (use_base & 1u) == (uint32_t)set;
-            cb0 = lhalf * 64; cb1 = 128 + lhalf * 64;
-          }
-          use_base += split ? 1u : 2u;
-          if (have) {
+          // Every group has two uses, one per half of the page tile, and set s takes half s: a tile pair fills all
+          // 128 columns of its slot (4 chunks per warp); the split tile (M = 128 over the pair, N = 128) fills 64
+          // columns, lanes 0-63 = this CTA's rows x tile columns [s*128, +64), lanes 64-127 = the same rows x the next 64.
+          const uint32_t my_use = use_base + (uint32_t)set;
+          const int nch = split ? 2 : 4;
+          const int cb0 = split ? set * 128 + lhalf * 64 : set * 128;
+          use_base += 2u;
+          {
             const uint32_t slot = my_use & (NACC - 1);
             const long long ec0 = st_on ? clock64() : 0;
             mbar_wait_u32(acc_full_u + slot * 8, (my_use / NACC) & 1u);
@@ -486,27 +485,23 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             uint32_t v0[32], v1[32], v2[32], v3[32];
             tmem_ld32(taddr, v0);
             tmem_ld32(taddr + 32, v1);
-            tmem_ld32(taddr + 64, v2);
-            tmem_ld32(taddr + 96, v3);
+            if (!split) { tmem_ld32(taddr + 64, v2); tmem_ld32(taddr + 96, v3); }
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster_u32(acc_empty_l + slot * 8);    // slot back to the MMA warps
             if (st_on) { st_wait += ec1 - ec0; const long long hc = clock64() - ec1; st_hold += hc; if (split) { st_hold_split += hc; st_wait_split += ec1 - ec0; ++st_n_split; } }
             skip_to(cb0);
-            if (!DBG && (!live || pe > cb1 + 64)) {
+            if (!DBG && (!live || pe > cb0 + nch * 32)) {
               if (live) {                      // fast path: no page ends inside this warp's columns
                 m = max32(v0, m);
                 m = max32(v1, m);
-                m = max32(v2, m);
-                m = max32(v3, m);
+                if (!split) { m = max32(v2, m); m = max32(v3, m); }
               }
             } else {
               scan(v0, cb0);
               scan(v1, cb0 + 32);
-              skip_to(cb1);
-              scan(v2, cb1);
-              scan(v3, cb1 + 32);
+              if (!split) { scan(v2, cb0 + 64); scan(v3, cb0 + 96); }
             }
           }
           skip_to(NT);

@@ -107,3 +107,35 @@ def test_topk_workspace_sizes(native):
     c = lib.lis_topk_workspace_bytes(1, 500_000, 100)
     assert 0 < a < b and a < c
     assert lib.lis_topk_workspace_bytes(1, 100, 5000) == 0           # k out of range
+
+
+@pytest.mark.parametrize("n_tiles", list(range(1, 40)) + [64, 255, 256, 1000])
+def test_pass_plan_covers_every_tile_once(native, n_tiles):
+    """lis_maxsim_pass_plan (host-only): the passes add up to the tile count and only instantiated shapes appear."""
+    import ctypes as C
+
+    lib = native.load()
+    buf = (C.c_int32 * 1024)()
+    try:
+        for tun, allowed_pair, allowed_single in (((0, 0, 0, 0, 0), {2, 3, 4, 5, 6, 8, 10}, {1, 2, 3}),
+                                                  ((0, 0, 0, 0, 3), {2, 3, 4, 5, 6}, {1}),
+                                                  ((0, 10, 0, 0, 3), {2, 3, 4, 5, 6, 8, 10}, {1}),
+                                                  ((0, 4, 0, 0, 0), {2, 3, 4}, {1, 2, 3}),
+                                                  ((0, 0, 0, 0, 1), set(), {1, 2, 3}),
+                                                  ((128, 5, 0, 0, 1), set(), {1, 2, 3, 4, 5})):
+            native.check(lib.lis_set_tuning(*tun))
+            n = lib.lis_maxsim_pass_plan(n_tiles, buf, 1024)
+            assert n > 0
+            passes = [buf[i] for i in range(n)]
+            assert sum(abs(x) for x in passes) == n_tiles, (tun, passes)
+            for x in passes:
+                assert (-x in allowed_pair) if x < 0 else (x in allowed_single), (tun, passes)
+            assert lib.lis_maxsim_pass_plan(n_tiles, None, 0) == n
+    finally:
+        lib.lis_set_tuning(0, 0, 0, 0, 0)
+    # auto: one CTA per SM up to 3 tiles, CTA pairs from 4 on
+    n = lib.lis_maxsim_pass_plan(n_tiles, buf, 1024)
+    if n_tiles <= 3:
+        assert [buf[i] for i in range(n)] == [n_tiles]
+    elif n_tiles in (4, 5, 6, 8, 10):
+        assert [buf[i] for i in range(n)] == [-n_tiles]
