@@ -165,7 +165,7 @@ def workload_config(args, pages, note=None):
                     f"per GPU (128-d), full score matrix",
         "queries": NQ, "query_tokens": QTOK, "pages_per_gpu": pages, "page_tokens": PAGE_TOK, "dim": DIM,
         "sharding": f"pages x{args.gpus} (one shard of {pages} pages per GPU, no data-path collective)",
-        "l2": "inputs (26.4 GB/GPU) are larger than L2; no flush needed",
+        "l2": f"inputs ({pages * PAGE_TOK * DIM * 2 / 1e9:.1f} GB/GPU) are larger than L2; no flush needed",
     }
     if note:
         cfg["note"] = note
