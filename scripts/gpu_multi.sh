@@ -14,3 +14,8 @@ if [ "${BIG:-0}" = "1" ]; then
       bench.py --gpus $N --steps 5 --warmup 3 --pages 500000 --search-iters 200 --no-cpu > gpurun_out/multi_bench_big_$N.log 2>&1
   echo "bench_big exit $?"; tail -1 gpurun_out/multi_bench_big_$N.log | cut -c1-300; tail -1 gpurun_out/multi_bench_big_$N.log | grep -o '"search": {[^}]*}'
 fi
+if [ "${C3:-0}" = "1" ]; then
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 \
+      scripts/gpu_c3_sharded.py > gpurun_out/multi_c3_$N.log 2>&1
+  echo "c3_sharded exit $?"; grep '^{' gpurun_out/multi_c3_$N.log | cut -c1-420
+fi
