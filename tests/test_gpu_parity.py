@@ -87,6 +87,21 @@ def test_many_queries_multi_mtile(lis, oracle):
     check_both_modes(lis, oracle, q, p)
 
 
+def test_reference_mode_vs_torch_gpu_route(lis, oracle):
+    """The reference's loop run on the SAME GPU through torch (cuBLAS einsum + max + sum in bf16, what colpali-engine does
+    with device="cuda") against the fused kernel in round_mode="reference": within one bf16 step, >= 95 % bit-identical
+    (on the round-1 boxes all scores were bit-identical)."""
+    g = torch.Generator().manual_seed(77)
+    q = rand_unit(g, 32, 20, 128)
+    p = ragged(g, [1030] * 300 + [int(x) for x in torch.randint(200, 900, (212,), generator=g)])
+    want = oracle.score_multi_vector(q, p, device="cuda")
+    got = lis.score_multi_vector(q, p)
+    diff = (got - want).abs()
+    step = torch.maximum(bf16_step(want), torch.tensor(TOL_BF16))
+    assert (diff <= step).all(), diff.max().item()
+    assert (diff == 0).float().mean().item() >= 0.95
+
+
 def test_ragged_lists_and_zero_padding(lis, oracle):
     g = torch.Generator().manual_seed(3)
     q_lens = [5, 20, 33, 128, 130, 300, 1, 17]
