@@ -644,7 +644,10 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
               if (GRP > 3) scan(v3, cb + 96);
             }
           }
-          if (EH == 2 && half == 0) skip_to(NT);
+          // every warp closes ALL pages that end inside this tile before it moves on: a page ending exactly at the
+          // tile's last column followed by empty pages would otherwise be closed in this tile by the warps of
+          // column half 0 and in the next tile by those of half 1 -- different publication orders, mixed-up slots
+          skip_to(NT);
           rotate(m);
           p_next = pp;
           pend_next = ppend;

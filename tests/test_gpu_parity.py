@@ -102,6 +102,28 @@ def test_reference_mode_vs_torch_gpu_route(lis, oracle):
     assert (diff == 0).float().mean().item() >= 0.95
 
 
+def test_page_ending_on_tile_boundary_followed_by_empty_pages(lis, oracle):
+    """Regression (found by scripts/gpu_fuzz_pair.py): a page that ends exactly on a 256-row tile boundary, followed by
+    two or more empty pages, with several query tiles resident -- the warps of the two column halves used to close the
+    trailing empty page in different tiles, which mixed up the exchange slots of the single-CTA kernel."""
+    from importlib import import_module
+
+    N = import_module("multi-modal_colpali_b200._native")
+    lib = N.load()
+    g = torch.Generator().manual_seed(314)
+    qs = ragged(g, [20] * 19 + [4])                       # 384 rows = 3 query tiles
+    p_lens = [256, 0, 0, 100, 412, 0, 0, 0, 50, 206, 0, 0, 1024, 0, 0, 33]   # ends at rows 256, 768, 1024, 2048
+    ps = ragged(g, p_lens)
+    want = oracle.score_multi_vector_widened(qs, ps)
+    try:
+        for tun in ((0, 0, 1, 0, 1), (0, 2, 1, 0, 1), (128, 3, 1, 0, 1), (0, 0, 2, 0, 3), (0, 0, 0, 0, 0), (0, 0, 1, 0, 0)):
+            N.check(lib.lis_set_tuning(*tun))
+            got = lis.score_multi_vector(qs, ps, round_mode="f32")
+            assert (got - want).abs().max().item() <= TOL_F32, tun
+    finally:
+        lib.lis_set_tuning(0, 0, 0, 0, 0)
+
+
 def test_ragged_lists_and_zero_padding(lis, oracle):
     g = torch.Generator().manual_seed(3)
     q_lens = [5, 20, 33, 128, 130, 300, 1, 17]
