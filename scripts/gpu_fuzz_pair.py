@@ -36,8 +36,10 @@ for c in range(cases):
         n = {0: rint(1, 40), 1: rint(1, 3), 2: rint(60, 300), 3: 20}[style]
         n = min(n, left); q_lens.append(n); left -= n
     n_pages = rint(1, 900)
-    pstyle = rint(0, 3)
-    p_lens = [{0: rint(0, 60), 1: rint(200, 1100), 2: 1030, 3: rint(0, 3) * rint(0, 700)}[pstyle] for _ in range(n_pages)]
+    pstyle = rint(0, 5)          # 4, 5: tile-aligned lengths with many empty pages (the page-close order cases)
+    aligned = [0, 0, 0, 64, 128, 192, 256, 256, 320, 512, 1024]
+    p_lens = [{0: rint(0, 60), 1: rint(200, 1100), 2: 1030, 3: rint(0, 3) * rint(0, 700), 4: aligned[rint(0, 10)],
+               5: aligned[rint(0, 10)] + (rint(0, 9) == 0) * rint(1, 300)}[pstyle] for _ in range(n_pages)]
     bs = [128, 16, 7][rint(0, 2)]
     for j in range(0, n_pages, bs):          # the reference itself fails on a block of only empty pages (max over an empty dim)
         if max(p_lens[j:j + bs]) == 0:
