@@ -46,6 +46,17 @@ for i in range(32):
     idx.search([qs[i % 16]], 10)
 seq = (time.perf_counter() - t0) / 32
 emit({"case": "sequential_single_query", "pages": pages, "ms_per_query": seq * 1e3, "qps": 1 / seq})
+# what one coalesced pass costs as it grows (no threads: index.search on a list of n single queries of 16 tokens):
+# up to 3 query tiles run on one CTA per SM, 4+ tiles on CTA pairs
+qs80 = [unit(torch.randn(16, 128, generator=g)).to(torch.bfloat16) for _ in range(80)]
+for n in (1, 8, 16, 24, 32, 48, 64, 80):
+    for _ in range(3):
+        idx.search(qs80[:n], 10)
+    ts = []
+    for _ in range(12):
+        t0 = time.perf_counter(); idx.search(qs80[:n], 10); ts.append((time.perf_counter() - t0) * 1e3)
+    ts.sort()
+    emit({"case": "one_pass_n_queries", "pages": pages, "queries": n, "query_rows": 16 * n, "p50_ms": ts[6], "qps": n / (ts[6] * 1e-3)})
 for max_rows in (128, 256):
     b = lis.QueryBatcher(idx, max_rows=max_rows, max_wait_ms=0.5)
     lat = []
