@@ -17,6 +17,12 @@
  *   - lis_project_normalize  <- retrieval head inside model(**batch)         functions.py:795,839,888
  *                               (body: HF modeling_colpali.py:148-155)
  *   - lis_merge_topk         <- (no reference equivalent; merges per-GPU candidates after the allgather)
+ *   - lis_comm_*, lis_index_search_sharded
+ *                            <- (no reference equivalent: the reference is single-GPU, functions.py:1472; this is
+ *                               north_star's "each GPU scores its shard ... single NCCL allgather" search)
+ *   - lis_index_add_projected <- the ingestion loop functions.py:838-865 (model head -> tolist() -> HTTP upsert)
+ *   - lis_stream_scores      <- score_multi_vector with the corpus on the HOST, as the reference calls it
+ *                               (05_experiment02.py:213-214: ps is a CPU tensor, moved per 128-page block)
  */
 #ifndef LIS_H_
 #define LIS_H_
@@ -28,7 +34,7 @@
 extern "C" {
 #endif
 
-#define LIS_ABI_VERSION 1
+#define LIS_ABI_VERSION 2
 
 /* embedding width: VECTOR_SIZE = 128 (01_create_context_qdrant.py:70) */
 #define LIS_DIM 128
@@ -40,7 +46,8 @@ enum lis_status {
   LIS_E_INVALID = -1,     /* bad argument */
   LIS_E_CUDA = -2,        /* CUDA runtime / driver error */
   LIS_E_UNSUPPORTED = -3, /* valid request this build cannot serve (e.g. not an sm_100 device) */
-  LIS_E_NOMEM = -4
+  LIS_E_NOMEM = -4,
+  LIS_E_NCCL = -5         /* NCCL missing or a collective failed */
 };
 
 /* LIS_F32X2: fp32 embeddings held as two bf16 planes (hi = bf16(x), lo = bf16(x - hi)); index dtype only */
@@ -184,10 +191,17 @@ int lis_merge_topk(const float* cand_scores, const int64_t* cand_ids, int64_t nq
  *   i.e. torch Linear.weight);  bias device [128] dtype or NULL;  mask device [n_tok] integers of
  *   mask_itemsize bytes (1, 4 or 8: bool/uint8, int32, int64 attention masks are taken as they are)
  *   or NULL;  out device [n_tok,128] dtype.  hidden_dim % 64 == 0.
+ *   round_mode  LIS_ROUND_F32: bias, norm and scale applied to the fp32 accumulators, one rounding at the store
+ *               (the more accurate embedding).  LIS_ROUND_REFERENCE: what the reference's 16-bit model computes
+ *               (HF modeling_colpali.py:148-155): Linear output rounded to dtype, norm of the rounded values
+ *               rounded to dtype, quotient rounded to dtype.
+ *   dst_row     device int32 [n_tok] or NULL.  When given, token t is written to row dst_row[t] of `out` instead
+ *               of row t, and tokens with dst_row[t] < 0 are not written at all (ragged compaction of padded
+ *               encoder batches straight into a page store; see lis_index_add_projected).
  */
 int lis_project_normalize(const void* hidden, int64_t n_tok, int64_t hidden_dim, const void* weight,
-                          const void* bias, const void* mask, int mask_itemsize, int dtype, void* out,
-                          void* stream);
+                          const void* bias, const void* mask, int mask_itemsize, int dtype, int round_mode,
+                          const int32_t* dst_row, void* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Page index: the GPU-resident replacement for the Qdrant multivector collection.
@@ -234,12 +248,100 @@ int lis_index_dtype(const lis_index* idx);
 int lis_fill_synthetic_rows(void* dst, int64_t row0, int64_t n_rows, uint64_t seed, int dtype, void* stream);
 /* Search: packed queries (as for lis_maxsim_scores; for an LIS_F32X2 index `q` is the hi plane and
  * `q_lo` the lo plane, else q_lo = NULL) -> top-k (score, id) per query.
- * Requires n_seg == nq (no split queries) unless seg_first != NULL (device int32 [nq+1]).
- * Scratch is owned by the index and grown on demand (outside the timed path after warm-up). */
+ * seg_first == NULL states that segment s is query s (no query cut, none empty: QueryPlan.direct); otherwise
+ * seg_first is device int32 [nq+1] and the segments of each query are added up.
+ * Scratch is owned by the index and grown on demand (outside the timed path after warm-up).
+ * ONE search in flight per index: the scratch is shared, so concurrent calls on the same index are serialised
+ * by a lock inside the library and must use the same stream (different indexes are independent). */
 int lis_index_search(lis_index* idx, const void* q, const void* q_lo, int64_t q_rows, const int32_t* seg_lo,
                      const int32_t* seg_hi, const int32_t* mt_seg, int64_t n_seg, int64_t n_mtiles,
                      const int32_t* seg_first, int64_t nq, int round_mode, int k, float* out_scores,
                      int64_t* out_ids, void* stream);
+
+
+/* Ingestion fusion: K3 writes straight into the page store.  hidden device [n_pages, seq, hidden_dim]
+ * (a padded encoder batch), mask device [n_pages, seq] integers of mask_itemsize bytes (required: it defines which
+ * rows exist; left- and right-padded batches alike).  Row t of page b lands at
+ * store_row(b) + (number of kept tokens before t in page b); pad rows are never written; page b gets
+ * clamp = (kept < seq), i.e. the reference's zero-padding semantics for the dropped rows.  ids host int64
+ * [n_pages] or NULL.  Page lengths are computed on the device; one 8-byte read-back tells the host the new
+ * row count.  Not available for LIS_F32X2 indexes (the encoder head is 16-bit).  Synchronous on return. */
+int lis_index_add_projected(lis_index* idx, const void* hidden, int64_t n_pages, int64_t seq, int64_t hidden_dim,
+                            const void* weight, const void* bias, const void* mask, int mask_itemsize,
+                            int round_mode, const int64_t* ids, void* stream);
+/* Host copy of page lengths [first, first+n) (int32), e.g. after lis_index_add_projected. */
+int lis_index_page_lens(const lis_index* idx, int64_t first, int64_t n, int32_t* lens_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU, pages sharded by rank, ONE all-gather of the per-rank top-k per search.
+ * NCCL is bound at run time (dlopen libnccl.so.2).  Rank 0 creates the id and ships it to the other ranks by
+ * any means (torch.distributed broadcast, MPI, a file); every rank then calls lis_comm_init.
+ */
+#define LIS_COMM_ID_BYTES 128
+typedef struct lis_comm lis_comm;
+int lis_comm_unique_id(void* out, int bytes);            /* out: LIS_COMM_ID_BYTES bytes (an ncclUniqueId) */
+int lis_comm_init(lis_comm** out, const void* unique_id, int rank, int world, int device);   /* collective */
+void lis_comm_destroy(lis_comm* comm);
+int lis_comm_rank(const lis_comm* comm);
+int lis_comm_world(const lis_comm* comm);
+int lis_nccl_version(void);                              /* e.g. 22809; 0 when NCCL is not loadable */
+
+/* One-shot search, host in -> host out, synchronous: the call a server makes per request.
+ *   q          packed query rows [q_rows,128] in HOST or device memory: 16-bit rows of the index dtype, or float
+ *              rows for an LIS_F32X2 index (split into planes on the device)
+ *   seg_lo/seg_hi/mt_seg/seg_first   HOST arrays from lis_plan_queries (seg_first NULL = direct, see above)
+ *   comm       NULL or a 1-rank communicator: this index is the whole corpus.  Otherwise every rank calls with the
+ *              same queries and k; each scores its shard, K2's last pass writes the local (score, id) candidates
+ *              into the send buffer, ONE ncclAllGather, and the same tournament kernel merges world*k candidates
+ *              on every rank.  A rank whose shard is empty contributes padding.  Page ids must be globally unique.
+ *   out_scores HOST float [nq,k], out_ids HOST int64 [nq,k]: best first, ties by ascending id, (-inf,-1) padding.
+ *   stream     the stream on which a device-resident q was produced (ordering only).
+ * The whole device sequence (table/query upload, K1, segment sums, K2, all-gather, merge, result download) is
+ * captured into a CUDA graph per (query shape, k, corpus size) the first time it is seen and replayed afterwards
+ * on a stream owned by the index. */
+int lis_index_search_sharded(lis_index* idx, lis_comm* comm, const void* q, int64_t q_rows, const int32_t* seg_lo,
+                             const int32_t* seg_hi, const int32_t* mt_seg, int64_t n_seg, int64_t n_mtiles,
+                             const int32_t* seg_first, int64_t nq, int round_mode, int k, float* out_scores,
+                             int64_t* out_ids, void* stream);
+
+/* Persistence at storage speed: copy n_rows raw 16-bit rows of a plane between the store (from row0) and a file
+ * (from byte file_offset), through a pinned double buffer: every 64 MiB chunk is read by io_threads parallel
+ * pread()s while the previous chunk is DMA'd (load), or written while the next one is downloaded (save).  The file
+ * layout is exactly the HBM layout, so nothing is re-encoded.  Page tables travel separately (lis_index_set_tables).
+ * io_threads = 0 picks a default.  Synchronous on return. */
+int lis_index_load_rows(lis_index* idx, int plane, int64_t row0, int64_t n_rows, const char* path,
+                        int64_t file_offset, int io_threads, void* stream);
+int lis_index_save_rows(const lis_index* idx, int plane, int64_t row0, int64_t n_rows, const char* path,
+                        int64_t file_offset, int io_threads, void* stream);
+
+/* Remove page number `page` (position in the index, 0-based) from all future searches: its id becomes -1, which
+ * K2 treats as padding.  The rows stay in the store (append-only layout); re-adding the content under the same
+ * caller id is how an upsert replaces a point (functions.py:865 upserts by point id). */
+int lis_index_tombstone(lis_index* idx, int64_t page, void* stream);
+
+/* Introspection: number of cached search graphs; *captures / *replays (may be NULL) count since creation. */
+int64_t lis_index_graph_stats(const lis_index* idx, int64_t* captures, int64_t* replays);
+
+/* ---------------------------------------------------------------------------------------------
+ * Surface 1 with a HOST-resident corpus, as the reference calls it (05_experiment02.py:213-214).  The token rows
+ * stay where they are: they are cut into chunks of whole pages, each chunk goes through a pinned double buffer
+ * to the device on a copy stream, and K1 scores chunk i while chunk i+1 is in flight.
+ *   q, seg_*, mt_seg       device, as for lis_maxsim_scores
+ *   tokens_host            HOST [n_rows,128] 16-bit rows, pageable or pinned (a pinned source is DMA'd in place), or NULL
+ *   page_ptrs_host         HOST array of np HOST pointers, page p's rows at page_ptrs_host[p] (a Python list of per-page
+ *                          tensors, as create_document_embeddings returns it), or NULL -- exactly one of the two
+ *   p_offsets_host         HOST int64 [np+1] from 0 to n_rows, p_clamp_host HOST uint8 [np] or NULL
+ *   out                    device float [n_seg, ld_out]
+ *   chunk_rows             token rows per chunk (0 = default, 512 Ki rows = 128 MiB)
+ *   host_threads           threads gathering pageable rows into the pinned buffer (0 = default)
+ * Staging buffers (2 pinned + 2 device chunks) are kept per device between calls; lis_stream_release frees them.
+ * Synchronous on return. */
+int lis_stream_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, const int32_t* seg_hi,
+                      const int32_t* mt_seg, int64_t n_seg, int64_t n_mtiles, const void* tokens_host,
+                      const void* const* page_ptrs_host, int64_t n_rows, const int64_t* p_offsets_host,
+                      const uint8_t* p_clamp_host, int64_t np, int dtype, int round_mode, float* out,
+                      int64_t ld_out, int64_t chunk_rows, int host_threads, void* stream);
+void lis_stream_release(void);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,8 @@ LIS_E_INVALID = -1
 LIS_E_CUDA = -2
 LIS_E_UNSUPPORTED = -3
 LIS_E_NOMEM = -4
+LIS_E_NCCL = -5
+COMM_ID_BYTES = 128
 
 LIS_BF16 = 0
 LIS_F16 = 1
@@ -54,7 +56,7 @@ SIGNATURES = {
     "lis_topk_workspace_bytes": (_i64, [_i64, _i64, _i32]),
     "lis_topk": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp]),
     "lis_merge_topk": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp]),
-    "lis_project_normalize": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "lis_project_normalize": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "lis_index_create": (_i32, [C.POINTER(_vp), _i32, _i32, _i64, _i64]),
     "lis_index_destroy": (None, [_vp]),
     "lis_index_add": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
@@ -73,6 +75,22 @@ SIGNATURES = {
     "lis_index_dtype": (_i32, [_vp]),
     "lis_fill_synthetic_rows": (_i32, [_vp, _i64, _i64, C.c_uint64, _i32, _vp]),
     "lis_index_search": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "lis_index_add_projected": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "lis_index_page_lens": (_i32, [_vp, _i64, _i64, _vp, _vp]),
+    "lis_comm_unique_id": (_i32, [_vp, _i32]),
+    "lis_comm_init": (_i32, [C.POINTER(_vp), _vp, _i32, _i32, _i32]),
+    "lis_comm_destroy": (None, [_vp]),
+    "lis_comm_rank": (_i32, [_vp]),
+    "lis_comm_world": (_i32, [_vp]),
+    "lis_nccl_version": (_i32, []),
+    "lis_index_search_sharded": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "lis_index_load_rows": (_i32, [_vp, _i32, _i64, _i64, C.c_char_p, _i64, _i32, _vp]),
+    "lis_index_save_rows": (_i32, [_vp, _i32, _i64, _i64, C.c_char_p, _i64, _i32, _vp]),
+    "lis_index_tombstone": (_i32, [_vp, _i64, _vp]),
+    "lis_index_graph_stats": (_i64, [_vp, _vp, _vp]),
+    "lis_stream_scores": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp,
+                                 _i64, _i64, _i32, _vp]),
+    "lis_stream_release": (None, []),
 }
 
 _lib = None
@@ -98,7 +116,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.lis_abi_version() != 1:
+    if lib.lis_abi_version() != 2:
         raise RuntimeError("liblis.so ABI version mismatch; rebuild with LIS_REBUILD=1")
     _lib = lib
     return lib

@@ -16,7 +16,8 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "_lib"
 LIB = LIBDIR / "liblis.so"
-SOURCES = ["lis_maxsim.cu", "lis_maxsim_pair.cu", "lis_topk.cu", "lis_project.cu", "lis_index.cu"]
+SOURCES = ["lis_maxsim.cu", "lis_maxsim_pair.cu", "lis_topk.cu", "lis_project.cu", "lis_index.cu", "lis_comm.cu",
+           "lis_stream.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-DLIS_BUILD",
@@ -53,7 +54,7 @@ def build_variant(name: str, defines) -> Path:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stderr}")
         objs.append(obj)
     out = LIBDIR / f"liblis_{name}.so"
-    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *map(str, objs)],
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *map(str, objs), "-ldl"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stderr}")
@@ -84,7 +85,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     tmp = LIBDIR / "liblis.so.tmp"
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp), *map(str, objs)]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp), *map(str, objs), "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -26,6 +26,15 @@ struct Tuning {
 };
 extern Tuning g_tuning;
 
+// K2 tournament (lis_topk.cu).  seg_len > 0: row q of the input consists of blocks of seg_len candidates lying
+// seg_stride_s floats / seg_stride_i int64 apart (all-gathered per-rank candidate blocks).
+int run_tournament(const float* s, int64_t ld_s, const int64_t* ids, int64_t ld_ids, int64_t id_base, int64_t nq,
+                   int64_t n, int k, float* out_s, int64_t* out_id, void* ws, int64_t ws_bytes, cudaStream_t st,
+                   int seg_len, int64_t seg_stride_s, int64_t seg_stride_i);
+// ncclAllGather of `bytes` bytes per rank (lis_comm.cu)
+int comm_all_gather(lis_comm* c, const void* send, void* recv, size_t bytes, cudaStream_t st);
+Tuning tuning_snapshot();
+
 // Encode a 2-D row-major [rows, 128] 16-bit tensor with a (64 col x box_rows) box, 128-byte swizzle.
 int encode_rows_tmap(CUtensorMap* map, const void* base, int64_t rows, int box_rows, int dtype);
 int sm_count(int device);

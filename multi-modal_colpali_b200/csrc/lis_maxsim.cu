@@ -21,7 +21,12 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 std::atomic<int64_t> g_launches{0};
-Tuning g_tuning;
+Tuning g_tuning;   // experiment knobs: written under g_tuning_mu, read through tuning_snapshot()
+static std::mutex g_tuning_mu;
+Tuning tuning_snapshot() {
+  std::lock_guard<std::mutex> lock(g_tuning_mu);
+  return g_tuning;
+}
 static long long* g_stats = nullptr;
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -100,12 +105,12 @@ static int launch_maxsim(const Maps& m, const MaxSimArgs& a, int grid, cudaStrea
     return LIS_E_INVALID;
   }
   auto kern = maxsim_kernel<NT, G, EH, ATM, DBG, P>;
-  static bool configured[64] = {false};  // per template instantiation and device
+  static std::atomic<bool> configured[64];  // per template instantiation and device
   int dev = 0;
   LIS_CUDA_CHECK(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
+  if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
     LIS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
+    if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
   }
   kern<<<grid, kCtrlThreads + 128 * EH, smem, st>>>(m.q, m.p, m.q2, m.p2, a, ns);
   count_launch();
@@ -115,7 +120,7 @@ static int launch_maxsim(const Maps& m, const MaxSimArgs& a, int grid, cudaStrea
 
 // Instantiations.  SS form (A in shared memory): NT 256 x G 1..3, NT 128 x G 1..5.
 // TS form (A in tensor memory): 64*G + NACC*NT <= 512 columns -> NT 128 x G 1..4, NT 192 x G 1..2.
-static int dispatch_maxsim(int nt, int g, bool atm, const Maps& m, const MaxSimArgs& a, int grid,
+static int dispatch_maxsim(const Tuning& tn, int nt, int g, bool atm, const Maps& m, const MaxSimArgs& a, int grid,
                            cudaStream_t st, bool dbg = false, int planes = 1) {
   if (planes == 2) {  // split fp32: one resident M tile (2 planes) + 2 stages of 2-plane 128-row tiles
     if (g == 1) return launch_maxsim<128, 1, 2, false, false, 2>(m, a, grid, st);
@@ -128,7 +133,7 @@ static int dispatch_maxsim(int nt, int g, bool atm, const Maps& m, const MaxSimA
     if (nt == 128 && g == 1 && atm) return launch_maxsim<128, 1, 2, true, true>(m, a, grid, st);
     if (nt == 192 && g == 1 && atm) return launch_maxsim<192, 1, 2, true, true>(m, a, grid, st);
   }
-  const int eh = g_tuning.epi_halves ? g_tuning.epi_halves : 2;
+  const int eh = tn.epi_halves ? tn.epi_halves : 2;
 #define LIS_CASE(NT_, G_, ATM_)                                                                \
   if (nt == NT_ && g == G_ && atm == ATM_)                                                     \
     return eh == 2 ? launch_maxsim<NT_, G_, 2, ATM_, false>(m, a, grid, st)                    \
@@ -167,6 +172,7 @@ int lis_k1_stats(long long* device_buf) {
 }
 int lis_set_ablation(int mode) {
   LIS_REQUIRE(mode >= 0 && mode <= 4, "ablation mode must be in 0..4");
+  std::lock_guard<std::mutex> lock(g_tuning_mu);
   g_tuning.ablate = mode;
   return LIS_OK;
 }
@@ -197,6 +203,7 @@ int lis_set_tuning(int tile_n, int group, int max_ctas, int epi_halves, int a_op
     LIS_REQUIRE(group <= gm, "tile_n=%d a_operand=%d supports group <= %d", tile_n, a_operand, gm);
   }
   LIS_REQUIRE(!(tile_n == 256 && group > 3 && a_operand != 3), "tile_n=256 supports group <= 3 on a single CTA");
+  std::lock_guard<std::mutex> lock(g_tuning_mu);
   g_tuning.tile_n = tile_n;
   g_tuning.group = group;
   g_tuning.max_ctas = max_ctas;
@@ -303,18 +310,18 @@ static int current_device_sm_count() {
 // pipe.  Up to 3 M tiles stay resident (A 96 KB + 2 B stages of 64 KB); more tiles -> several
 // balanced passes (5 -> 3+2).  The TS form (queries in tensor memory, a_operand = 2) is functionally
 // identical and kept selectable; on a power-capped B200 it measured 3-8 % slower (sweep_r1_v4).
-static void choose_tiling(int64_t n_mtiles, int* nt, int* g, bool* atm) {
-  if (g_tuning.a_operand) *atm = g_tuning.a_operand == 2;
+static void choose_tiling(const Tuning& tn, int64_t n_mtiles, int* nt, int* g, bool* atm) {
+  if (tn.a_operand) *atm = tn.a_operand == 2;
   else *atm = false;
-  if (g_tuning.tile_n) *nt = g_tuning.tile_n;
+  if (tn.tile_n) *nt = tn.tile_n;
   else *nt = *atm ? 128 : 256;
   int gmax = max_group(*nt, *atm);
   if (gmax == 0) {  // inconsistent override: fall back to the default tile for this form
     *nt = *atm ? 128 : 256;
     gmax = max_group(*nt, *atm);
   }
-  if (g_tuning.group) {
-    *g = std::min(g_tuning.group, gmax);
+  if (tn.group) {
+    *g = std::min(tn.group, gmax);
     return;
   }
   const int64_t passes = (n_mtiles + gmax - 1) / gmax;
@@ -323,16 +330,16 @@ static void choose_tiling(int64_t n_mtiles, int* nt, int* g, bool* atm) {
 
 // Pass plan: which kernel form takes how many query tiles in each pass over the store.
 struct Pass { bool pair; int n; };
-static void build_pass_plan(int64_t n_mtiles, bool must_single, int g_single, std::vector<Pass>& plan) {
+static void build_pass_plan(const Tuning& tn, int64_t n_mtiles, bool must_single, int g_single, std::vector<Pass>& plan) {
   plan.clear();
-  const bool forced_single = must_single || g_tuning.a_operand == 1 || g_tuning.a_operand == 2 ||
-                             g_tuning.tile_n != 0 || g_tuning.group == 1;
+  const bool forced_single = must_single || tn.a_operand == 1 || tn.a_operand == 2 ||
+                             tn.tile_n != 0 || tn.group == 1;
   const int g = g_single;
   if (forced_single) {
     for (int64_t t = 0; t < n_mtiles; t += g) plan.push_back({false, (int)std::min<int64_t>(g, n_mtiles - t)});
-  } else if (g_tuning.a_operand == 3) {
+  } else if (tn.a_operand == 3) {
     // experiments: CTA pairs only, balanced passes of at most `group` tiles (a leftover single tile runs on one CTA)
-    const int gmax = g_tuning.group ? std::min(std::max(g_tuning.group, 2), 10) : 6;
+    const int gmax = tn.group ? std::min(std::max(tn.group, 2), 10) : 6;
     const int64_t passes = (n_mtiles + gmax - 1) / gmax;
     int gp = (int)((n_mtiles + passes - 1) / passes);
     if (gp == 7 || gp == 9) ++gp;                       // 7 and 9 resident tiles are not instantiated
@@ -352,7 +359,7 @@ static void build_pass_plan(int64_t n_mtiles, bool must_single, int g_single, st
     // even tile counts being the efficient ones (no split tile); 8 and 10 tiles amortise the page stream a little more.
     static const float cost_single[4] = {0.f, 2.65f, 4.00f, 5.28f};
     static const float cost_pair[11] = {0.f, 0.f, 4.05f, 5.73f, 6.58f, 8.83f, 9.30f, 0.f, 12.33f, 0.f, 15.20f};   // 0 = not instantiated
-    const int gcap = g_tuning.group ? g_tuning.group : 10;    // group = most tiles a pass may hold
+    const int gcap = tn.group ? tn.group : 10;    // group = most tiles a pass may hold
     std::vector<float> best((size_t)n_mtiles + 1, 1e30f);
     std::vector<int8_t> choice((size_t)n_mtiles + 1, 0);       // +n = single pass of n tiles, -n = pair pass
     best[0] = 0.f;
@@ -376,6 +383,7 @@ static int maxsim_impl(const void* q, const void* q_lo, int64_t q_rows, const in
                        const void* tokens_lo, int64_t n_rows, const int64_t* p_offsets, const uint8_t* p_clamp,
                        int64_t np, int dtype, int round_mode, float* out, int64_t ld_out, void* stream) {
   const int planes = q_lo ? 2 : 1;
+  const Tuning tn = tuning_snapshot();   // one consistent view of the experiment knobs per call
   LIS_REQUIRE(q && seg_lo && seg_hi && mt_seg && p_offsets && out, "maxsim: null pointer");
   LIS_REQUIRE(dtype == LIS_BF16 || dtype == LIS_F16, "maxsim: dtype must be bf16 or f16");
   LIS_REQUIRE(round_mode >= 0 && round_mode <= 3, "bad round_mode");
@@ -394,10 +402,10 @@ static int maxsim_impl(const void* q, const void* q_lo, int64_t q_rows, const in
   int nt, g;
   bool atm;
   if (planes == 2) { nt = 128; g = 1; atm = false; }
-  else choose_tiling(n_mtiles, &nt, &g, &atm);
+  else choose_tiling(tn, n_mtiles, &nt, &g, &atm);
   std::vector<Pass> plan;
-  build_pass_plan(n_mtiles, planes == 2 || n_rows == 0 || sms < 2, g, plan);
-  if (planes != 2 && !(g_tuning.a_operand == 1 || g_tuning.a_operand == 2 || g_tuning.tile_n != 0)) { nt = 256; atm = false; }
+  build_pass_plan(tn, n_mtiles, planes == 2 || n_rows == 0 || sms < 2, g, plan);
+  if (planes != 2 && !(tn.a_operand == 1 || tn.a_operand == 2 || tn.tile_n != 0)) { nt = 256; atm = false; }
   bool pair = false;
   for (const Pass& ps : plan) pair = pair || ps.pair;
   Maps m;   // single-CTA form: 128-row query box, nt-row page box
@@ -432,10 +440,10 @@ static int maxsim_impl(const void* q, const void* q_lo, int64_t q_rows, const in
   }
 
   int grid = sms;
-  if (g_tuning.max_ctas > 0) grid = std::min(grid, g_tuning.max_ctas);
+  if (tn.max_ctas > 0) grid = std::min(grid, tn.max_ctas);
   grid = (int)std::min<int64_t>(grid, std::max<int64_t>(np, 1));
   int grid_pair = sms & ~1;
-  if (g_tuning.max_ctas > 0) grid_pair = std::max(2, std::min(grid_pair, g_tuning.max_ctas & ~1));
+  if (tn.max_ctas > 0) grid_pair = std::max(2, std::min(grid_pair, tn.max_ctas & ~1));
   grid_pair = (int)std::min<int64_t>(grid_pair, 2 * std::max<int64_t>(np, 1));
 
   int64_t mt0 = 0;
@@ -456,7 +464,7 @@ static int maxsim_impl(const void* q, const void* q_lo, int64_t q_rows, const in
     a.n_mt = ps.n;
     a.round_mode = round_mode;
     a.is_bf16 = dtype == LIS_BF16;
-    a.ablate = g_tuning.ablate;
+    a.ablate = tn.ablate;
     a.stats = g_stats;
     if (ps.pair) {
       rc = dispatch_maxsim_pair(mp.q, mp.p, a, grid_pair, st, false);
@@ -464,7 +472,7 @@ static int maxsim_impl(const void* q, const void* q_lo, int64_t q_rows, const in
       // the instantiation whose group equals this pass's tile count
       rc = single_maps();
       if (rc) return rc;
-      rc = dispatch_maxsim(nt, a.n_mt, atm, m, a, grid, st, false, planes);
+      rc = dispatch_maxsim(tn, nt, a.n_mt, atm, m, a, grid, st, false, planes);
     }
     if (rc) return rc;
     mt0 += ps.n;
@@ -474,11 +482,12 @@ static int maxsim_impl(const void* q, const void* q_lo, int64_t q_rows, const in
 
 int lis_maxsim_pass_plan(int64_t n_mtiles, int32_t* passes, int cap) {
   LIS_REQUIRE(n_mtiles > 0 && (cap == 0 || passes), "lis_maxsim_pass_plan: bad arguments");
+  const Tuning tn = tuning_snapshot();
   int nt, g;
   bool atm;
-  choose_tiling(n_mtiles, &nt, &g, &atm);
+  choose_tiling(tn, n_mtiles, &nt, &g, &atm);
   std::vector<Pass> plan;
-  build_pass_plan(n_mtiles, false, g, plan);
+  build_pass_plan(tn, n_mtiles, false, g, plan);
   for (size_t i = 0; i < plan.size() && (int)i < cap; ++i) passes[i] = plan[i].pair ? -plan[i].n : plan[i].n;
   return (int)plan.size();
 }
@@ -574,7 +583,7 @@ int lis_debug_sim_tile(const void* q, int64_t q_rows, const void* tokens, int64_
   a.stats = nullptr;
   a.q = q;
   a.q_rows = q_rows;
-  rc = dispatch_maxsim(tile_n, 1, a_in_tmem != 0, m, a, 1, st, true);
+  rc = dispatch_maxsim(tuning_snapshot(), tile_n, 1, a_in_tmem != 0, m, a, 1, st, true);
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(scratch);
   if (rc) return rc;

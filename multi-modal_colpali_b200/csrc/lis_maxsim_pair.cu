@@ -22,12 +22,12 @@ static int launch_pair(const CUtensorMap& q, const CUtensorMap& p, const MaxSimA
   }
   const int smem = a_bytes + ns * stage + kPairTail;
   auto kern = maxsim_pair_kernel<NF, ODD, DBG>;
-  static bool configured[64] = {false};
+  static std::atomic<bool> configured[64];
   int dev = 0;
   LIS_CUDA_CHECK(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
+  if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
     LIS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
+    if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);

@@ -26,11 +26,16 @@ struct ProjectArgs {
   int64_t n_tok;
   int32_t kblocks;      // hidden_dim / 64
   int32_t is_bf16;
+  int32_t round_ref;    // 1 = round the Linear output, the norm and the quotient to the 16-bit dtype like the reference model
+  const int32_t* dst_row;  // [n_tok] destination row of each token in `out`, < 0 = drop; null = identity
 };
 
 __device__ __forceinline__ float load16(const void* p, int i, int is_bf16) {
   return is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i])
                  : __half2float(reinterpret_cast<const __half*>(p)[i]);
+}
+__device__ __forceinline__ float round16(float x, int is_bf16) {
+  return is_bf16 ? __bfloat162float(__float2bfloat16_rn(x)) : __half2float(__float2half_rn(x));
 }
 __device__ __forceinline__ uint32_t pack16(float a, float b, int is_bf16) {
   if (is_bf16) {
@@ -121,6 +126,7 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * kPOut;
       const int64_t tok = tile * kPTile + row;
+      const int rr = args.round_ref, bf = args.is_bf16;
       float ss = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -129,11 +135,15 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float x = __uint_as_float(v[i]) + sbias[c * 32 + i];
+          float x = __uint_as_float(v[i]) + sbias[c * 32 + i];
+          if (rr) x = round16(x, bf);      // the reference's Linear returns the model dtype
           ss = fmaf(x, x, ss);
         }
       }
-      const float nrm = sqrtf(ss);
+      float nrm = sqrtf(ss);
+      if (rr) nrm = round16(nrm, bf);      // x.norm() of a 16-bit tensor: fp32 accumulation, 16-bit result
+      int64_t drow = tok;
+      if (args.dst_row != nullptr && tok < args.n_tok) drow = __ldg(args.dst_row + tok);
       float m = 1.f;
       if (args.mask != nullptr && tok < args.n_tok) {
         bool on;
@@ -147,17 +157,18 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
         uint32_t v[32];
         tmem_ld32(taddr + c * 32, v);
         tmem_ld_wait();
-        if (tok < args.n_tok) {
-          uint4* dst = reinterpret_cast<uint4*>(static_cast<uint8_t*>(args.out) + tok * 256 + c * 64);
+        if (tok < args.n_tok && drow >= 0) {
+          uint4* dst = reinterpret_cast<uint4*>(static_cast<uint8_t*>(args.out) + drow * 256 + c * 64);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint32_t w[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int i = j * 8 + e * 2;
-              const float x0 = (__uint_as_float(v[i]) + sbias[c * 32 + i]) / nrm * m;
-              const float x1 = (__uint_as_float(v[i + 1]) + sbias[c * 32 + i + 1]) / nrm * m;
-              w[e] = pack16(x0, x1, args.is_bf16);
+              float x0 = __uint_as_float(v[i]) + sbias[c * 32 + i];
+              float x1 = __uint_as_float(v[i + 1]) + sbias[c * 32 + i + 1];
+              if (rr) { x0 = round16(x0, bf); x1 = round16(x1, bf); }
+              w[e] = pack16(x0 / nrm * m, x1 / nrm * m, bf);
             }
             dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
           }
@@ -211,8 +222,9 @@ static int encode_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t c
 using namespace lis;
 
 extern "C" int lis_project_normalize(const void* hidden, int64_t n_tok, int64_t hidden_dim, const void* weight,
-                                     const void* bias, const void* mask, int mask_itemsize, int dtype, void* out,
-                                     void* stream) {
+                                     const void* bias, const void* mask, int mask_itemsize, int dtype,
+                                     int round_mode, const int32_t* dst_row, void* out, void* stream) {
+  LIS_REQUIRE(round_mode == LIS_ROUND_F32 || round_mode == LIS_ROUND_REFERENCE, "round_mode must be 0 (f32) or 1 (reference)");
   LIS_REQUIRE(mask == nullptr || mask_itemsize == 1 || mask_itemsize == 4 || mask_itemsize == 8,
               "mask_itemsize must be 1, 4 or 8");
   LIS_REQUIRE(hidden && weight && out, "lis_project_normalize: null pointer");
@@ -232,15 +244,17 @@ extern "C" int lis_project_normalize(const void* hidden, int64_t n_tok, int64_t 
   LIS_REQUIRE(sms > 0, "no CUDA device");
   const int ns = 6;
   const int smem = 1024 + ns * kPStageBytes + 1024;
-  static bool configured[64] = {false};
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
+  static std::atomic<bool> configured[64];
+  if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
     LIS_CUDA_CHECK(cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
+    if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
   }
   ProjectArgs a;
   a.bias = bias; a.mask = mask; a.mask_size = mask_itemsize; a.out = out; a.n_tok = n_tok;
   a.kblocks = (int32_t)(hidden_dim / 64);
   a.is_bf16 = dtype == LIS_BF16;
+  a.round_ref = round_mode == LIS_ROUND_REFERENCE;
+  a.dst_row = dst_row;
   const int64_t ntiles = (n_tok + kPTile - 1) / kPTile;
   const int grid = (int)std::min<int64_t>(sms, ntiles);
   project_kernel<<<grid, kPThreads, smem, (cudaStream_t)stream>>>(th, tw, a, ns);

@@ -25,11 +25,13 @@ __device__ __forceinline__ bool better(float sa, int64_t ia, float sb, int64_t i
 // One tournament pass.  Input row q: n candidates (score s[q*ld_s + i]; id = ids ? ids[q*ld_ids + i]
 // : id_base + i; ld_ids == 0 shares one id row between queries).  Output: chunk c of row q writes its
 // best k to (out_s, out_id)[q*out_ld + c*k ...]; with final != 0 padding is converted to (-inf, -1).
+// seg_len > 0: the input row is cut into blocks of seg_len candidates that lie seg_stride_s floats / seg_stride_i
+// int64 apart (the all-gathered per-rank [nq, k] candidate blocks: block w of row q starts at w * stride + q * ld).
 template <int kChunk, int kTopkThreads>
 __global__ void __launch_bounds__(kTopkThreads)
 topk_pass_kernel(const float* __restrict__ s, int64_t ld_s, const int64_t* __restrict__ ids, int64_t ld_ids,
                  int64_t id_base, int64_t n, int k, float* __restrict__ out_s, int64_t* __restrict__ out_id,
-                 int64_t out_ld, int final_pass) {
+                 int64_t out_ld, int final_pass, int seg_len, int64_t seg_stride_s, int64_t seg_stride_i) {
   extern __shared__ __align__(16) uint8_t topk_smem[];
   int64_t* sid = reinterpret_cast<int64_t*>(topk_smem);                    // [kChunk]
   float* ssc = reinterpret_cast<float*>(topk_smem + sizeof(int64_t) * kChunk);  // [kChunk]
@@ -42,8 +44,14 @@ topk_pass_kernel(const float* __restrict__ s, int64_t ld_s, const int64_t* __res
     float sc = -INFINITY;
     int64_t id = kPadId;
     if (col < n) {
-      sc = __ldg(s + q * ld_s + col);
-      id = ids ? __ldg(ids + q * ld_ids + col) : id_base + col;
+      int64_t so = q * ld_s + col, io = q * ld_ids + col;
+      if (seg_len > 0) {
+        const int64_t w = col / seg_len, j = col - w * seg_len;
+        so = w * seg_stride_s + q * ld_s + j;
+        io = w * seg_stride_i + q * ld_ids + j;
+      }
+      sc = __ldg(s + so);
+      id = ids ? __ldg(ids + io) : id_base + col;
       if (sc != sc) sc = -INFINITY;          // NaN never wins
       if (id < 0) { sc = -INFINITY; id = kPadId; }  // padding from a short shard
     }
@@ -81,22 +89,22 @@ topk_pass_kernel(const float* __restrict__ s, int64_t ld_s, const int64_t* __res
 static inline int64_t chunks_of(int64_t n, int chunk) { return (n + chunk - 1) / chunk; }
 static inline int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
 
-static int run_tournament(const float* s, int64_t ld_s, const int64_t* ids, int64_t ld_ids, int64_t id_base,
-                          int64_t nq, int64_t n, int k, float* out_s, int64_t* out_id, void* ws,
-                          int64_t ws_bytes, cudaStream_t st) {
+int run_tournament(const float* s, int64_t ld_s, const int64_t* ids, int64_t ld_ids, int64_t id_base,
+                   int64_t nq, int64_t n, int k, float* out_s, int64_t* out_id, void* ws,
+                   int64_t ws_bytes, cudaStream_t st, int seg_len, int64_t seg_stride_s, int64_t seg_stride_i) {
   LIS_REQUIRE(k >= 1 && k <= LIS_MAX_K, "k=%d out of range 1..%d", k, LIS_MAX_K);
   LIS_REQUIRE(nq >= 1 && nq <= 65535, "nq=%lld out of range", (long long)nq);
   LIS_REQUIRE(n >= 1, "no candidates");
   LIS_REQUIRE(s && out_s && out_id, "null pointer");
   const int chunk = chunk_for(k);
   const int smem = chunk * (int)(sizeof(int64_t) + sizeof(float));
-  static bool configured[64] = {false};
+  static std::atomic<bool> configured[64];   // zero-initialised; setting the attribute twice is harmless
   int dev = 0;
   LIS_CUDA_CHECK(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
+  if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
     LIS_CUDA_CHECK(cudaFuncSetAttribute(topk_pass_kernel<4096, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         4096 * (int)(sizeof(int64_t) + sizeof(float))));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
+    if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
   }
   // ping-pong buffers carved from the workspace
   const int64_t c0 = chunks_of(n, chunk);
@@ -123,13 +131,16 @@ static int run_tournament(const float* s, int64_t ld_s, const int64_t* ids, int6
     const int64_t o_ld = last ? k : nc * k;
     dim3 grid((unsigned)nc, (unsigned)nq);
     if (chunk == 1024)
-      topk_pass_kernel<1024, 256><<<grid, 256, smem, st>>>(in_s, in_ld, in_i, in_ldi, base, in_n, k, o_s, o_i, o_ld, last ? 1 : 0);
+      topk_pass_kernel<1024, 256><<<grid, 256, smem, st>>>(in_s, in_ld, in_i, in_ldi, base, in_n, k, o_s, o_i, o_ld, last ? 1 : 0,
+                                                           seg_len, seg_stride_s, seg_stride_i);
     else
-      topk_pass_kernel<4096, 512><<<grid, 512, smem, st>>>(in_s, in_ld, in_i, in_ldi, base, in_n, k, o_s, o_i, o_ld, last ? 1 : 0);
+      topk_pass_kernel<4096, 512><<<grid, 512, smem, st>>>(in_s, in_ld, in_i, in_ldi, base, in_n, k, o_s, o_i, o_ld, last ? 1 : 0,
+                                                           seg_len, seg_stride_s, seg_stride_i);
     count_launch();
     LIS_CUDA_CHECK(cudaGetLastError());
     if (last) break;
     in_s = o_s; in_i = o_i; in_ld = o_ld; in_ldi = o_ld; in_n = o_ld; base = 0;
+    seg_len = 0;   // survivors are plain rows
     ++pass;
   }
   return LIS_OK;
@@ -158,7 +169,7 @@ int lis_topk(const float* scores, int64_t ld, int64_t nq, int64_t np, const int6
              void* stream) {
   LIS_REQUIRE(ld >= np, "lis_topk: ld < np");
   return run_tournament(scores, ld, ids, 0, id_base, nq, np, k, out_scores, out_ids, workspace,
-                        workspace_bytes, (cudaStream_t)stream);
+                        workspace_bytes, (cudaStream_t)stream, 0, 0, 0);
 }
 
 int lis_merge_topk(const float* cand_scores, const int64_t* cand_ids, int64_t nq, int64_t n_cand, int k,
@@ -166,7 +177,7 @@ int lis_merge_topk(const float* cand_scores, const int64_t* cand_ids, int64_t nq
                    void* stream) {
   LIS_REQUIRE(cand_ids, "lis_merge_topk: cand_ids is null");
   return run_tournament(cand_scores, n_cand, cand_ids, n_cand, 0, nq, n_cand, k, out_scores, out_ids,
-                        workspace, workspace_bytes, (cudaStream_t)stream);
+                        workspace, workspace_bytes, (cudaStream_t)stream, 0, 0, 0);
 }
 
 }  // extern "C"

@@ -14,12 +14,31 @@ from . import _native as N
 from .scoring import _DTYPES, _stream
 
 
+_ROUND = {"f32": N.ROUND_F32, "reference": N.ROUND_REFERENCE}
+
+
+def mask_for_kernel(attention_mask: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    """Flat attention mask in a form K3 reads as it is (1-, 4- or 8-byte integers)."""
+    m = attention_mask.reshape(-1).to(dev).contiguous()
+    if m.dtype == torch.bool:
+        m = m.view(torch.uint8)
+    if m.element_size() not in (1, 4, 8) or m.is_floating_point():
+        m = (m != 0).view(torch.uint8)
+    return m
+
+
 def project_normalize(hidden: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
-                      attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      attention_mask: Optional[torch.Tensor] = None, *, round_mode: str = "reference") -> torch.Tensor:
     """``hidden [..., n_tok, H]`` (CUDA, bf16/fp16), ``weight [128, H]`` (``nn.Linear.weight``),
     ``bias [128]`` or None, ``attention_mask [..., n_tok]`` (any integer/bool dtype) or None
-    -> ``[..., n_tok, 128]`` unit-norm rows, zeroed where the mask is 0, in the input dtype."""
+    -> ``[..., n_tok, 128]`` unit-norm rows, zeroed where the mask is 0, in the input dtype.
+
+    ``round_mode="reference"`` (default) rounds where the reference's 16-bit model rounds (Linear output, norm,
+    quotient: HF modeling_colpali.py:149-152), so the stored embedding is the one the reference would store;
+    ``"f32"`` normalises the fp32 accumulators and rounds once (closer to the exact unit vector)."""
     lib = N.load()
+    if round_mode not in _ROUND:
+        raise ValueError(f"round_mode must be one of {sorted(_ROUND)}")
     if not hidden.is_cuda:
         raise RuntimeError("project_normalize runs on an sm_100 GPU only; there is no CPU fallback")
     dt = hidden.dtype
@@ -37,15 +56,11 @@ def project_normalize(hidden: torch.Tensor, weight: torch.Tensor, bias: Optional
     if attention_mask is not None:
         if attention_mask.shape != lead:
             raise ValueError("attention_mask must match hidden's leading dimensions")
-        m = attention_mask.reshape(-1).to(dev).contiguous()
-        if m.dtype == torch.bool:
-            m = m.view(torch.uint8)
-        if m.element_size() not in (1, 4, 8) or m.is_floating_point():
-            m = (m != 0).view(torch.uint8)
+        m = mask_for_kernel(attention_mask, dev)
     out = torch.empty((h2.shape[0], N.DIM), dtype=dt, device=dev)
     with torch.cuda.device(dev):
         N.check(lib.lis_project_normalize(h2.data_ptr(), h2.shape[0], hdim, w.data_ptr(),
                                           None if b is None else b.data_ptr(), None if m is None else m.data_ptr(),
-                                          0 if m is None else m.element_size(), _DTYPES[dt], out.data_ptr(),
-                                          _stream(dev)))
+                                          0 if m is None else m.element_size(), _DTYPES[dt], _ROUND[round_mode],
+                                          None, out.data_ptr(), _stream(dev)))
     return out.reshape(*lead, N.DIM)

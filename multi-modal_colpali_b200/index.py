@@ -19,7 +19,7 @@ import torch
 
 from . import _native as N
 from .scoring import (TensorOrList, _DTYPES, _ROUND, _as_list, _check_rows, _stream, clamp_flags,
-                      pack_queries, resolve_device)
+                      pack_queries, plan_queries, resolve_device)
 
 _TORCH_DTYPE = {N.LIS_BF16: torch.bfloat16, N.LIS_F16: torch.float16}
 
@@ -42,6 +42,12 @@ class LateInteractionIndex:
         N.check(self._lib.lis_index_create(C.byref(self._h), self.device.index, code,
                                            int(capacity_rows), int(capacity_pages)))
         self.payloads: Dict[int, Any] = {}
+        self._cap = (int(capacity_rows), int(capacity_pages))
+
+    @property
+    def capacity(self) -> Tuple[int, int]:
+        """(token rows, pages) the HBM store can hold before :meth:`reserve` has to grow it."""
+        return self._cap
 
     # -- lifetime ---------------------------------------------------------------------------------
     def close(self) -> None:
@@ -129,14 +135,51 @@ class LateInteractionIndex:
 
     def add_from_hidden(self, hidden: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
                         attention_mask: torch.Tensor, ids: Optional[Sequence[int]] = None,
-                        payloads: Optional[Sequence[Any]] = None) -> np.ndarray:
-        """Ingestion fusion: encoder hidden states ``[B, S, H]`` -> fused projection + L2-normalise +
-        mask (K3) -> ragged page store, in HBM all the way (replaces ``embedding.tolist()`` + HTTP upsert,
-        functions.py:843-865)."""
-        from .head import project_normalize
+                        payloads: Optional[Sequence[Any]] = None, round_mode: str = "reference") -> np.ndarray:
+        """Ingestion fusion: encoder hidden states ``[B, S, H]`` -> K3 (projection + L2-normalise +
+        mask) whose epilogue writes every kept row at ``store_row(page) + exclusive_prefix(mask)`` of the ragged
+        page store.  No dense ``[B, S, 128]`` tensor, no gather, no copy: page lengths, clamp flags and destination
+        rows are computed on the device (``lis_index_add_projected``); replaces ``model head -> tolist() -> HTTP
+        upsert`` (functions.py:838-865)."""
+        from .head import _ROUND as _HEAD_ROUND, mask_for_kernel
 
-        emb = project_normalize(hidden.to(self.device), weight, bias, attention_mask)
-        return self.add_padded(emb, attention_mask.to(self.device), ids=ids, payloads=payloads)
+        if hidden.dim() != 3 or attention_mask.shape != hidden.shape[:2]:
+            raise ValueError("expected hidden [B, S, H] and attention_mask [B, S]")
+        if self.dtype not in _DTYPES:
+            raise NotImplementedError("add_from_hidden: the encoder head is 16-bit; use a bf16/fp16 index")
+        if round_mode not in _HEAD_ROUND:
+            raise ValueError(f"round_mode must be one of {sorted(_HEAD_ROUND)}")
+        n, s_pad, hdim = hidden.shape
+        if weight.shape != (N.DIM, hdim):
+            raise ValueError(f"weight must be [{N.DIM}, {hdim}], got {tuple(weight.shape)}")
+        first = len(self)
+        id_arr = np.arange(first, first + n, dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
+        if id_arr.shape != (n,):
+            raise ValueError("ids must have one entry per page")
+        if payloads is not None and len(payloads) != n:
+            raise ValueError("payloads must have one entry per page")
+        h = hidden.to(device=self.device, dtype=self.dtype).contiguous()
+        w = weight.to(device=self.device, dtype=self.dtype).contiguous()
+        b = None if bias is None else bias.to(device=self.device, dtype=self.dtype).contiguous()
+        m = mask_for_kernel(attention_mask, self.device)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.lis_index_add_projected(self._h, h.data_ptr(), n, s_pad, hdim, w.data_ptr(),
+                                                      None if b is None else b.data_ptr(), m.data_ptr(),
+                                                      m.element_size(), _HEAD_ROUND[round_mode], id_arr.ctypes.data,
+                                                      _stream(self.device)))
+        if payloads is not None:
+            for i, pay in zip(id_arr.tolist(), payloads):
+                self.payloads[i] = pay
+        return id_arr
+
+    def page_lens(self, first: int = 0, n: Optional[int] = None) -> np.ndarray:
+        """Token rows of pages ``[first, first+n)`` (int32, host)."""
+        n = len(self) - first if n is None else n
+        out = np.zeros(max(n, 0), np.int32)
+        if n > 0:
+            with torch.cuda.device(self.device):
+                N.check(self._lib.lis_index_page_lens(self._h, int(first), int(n), out.ctypes.data, _stream(self.device)))
+        return out
 
     def fill_synthetic(self, n_pages: int, page_len: Union[int, Sequence[int]], seed: int, id_base: int = 0) -> None:
         """Append unit-norm pseudo-random pages generated on the device (benchmarks; see lis.h)."""
@@ -159,76 +202,176 @@ class LateInteractionIndex:
             N.check(self._lib.lis_index_read_rows(self._h, int(row0), int(n_rows), out.data_ptr(), _stream(self.device)))
         return out
 
+    # -- capacity / removal -------------------------------------------------------------------------
+    def reserve(self, capacity_rows: int, capacity_pages: int) -> None:
+        """Grow the HBM store to at least the given capacities (device-to-device copy of the row planes; the old
+        store is released afterwards, so twice the current size is resident for a moment)."""
+        rows, n = self.num_rows, len(self)
+        cap_r, cap_p = max(int(capacity_rows), rows, 1), max(int(capacity_pages), n, 1)
+        code = N.LIS_F32X2 if self.dtype == torch.float32 else _DTYPES[self.dtype]
+        new_h = C.c_void_p()
+        N.check(self._lib.lis_index_create(C.byref(new_h), self.device.index, code, cap_r, cap_p))
+        try:
+            with torch.cuda.device(self.device):
+                st = _stream(self.device)
+                if rows:
+                    N.check(self._lib.lis_index_write_rows(new_h, 0, 0, rows, self._lib.lis_index_tokens(self._h), st))
+                    if self.dtype == torch.float32:
+                        N.check(self._lib.lis_index_write_rows(new_h, 1, 0, rows, self._lib.lis_index_tokens_lo(self._h), st))
+                if n:
+                    off, ids, clamp = self.page_tables()
+                    N.check(self._lib.lis_index_set_tables(new_h, off.ctypes.data, ids.ctypes.data, clamp.ctypes.data, n, st))
+        except BaseException:
+            self._lib.lis_index_destroy(new_h)
+            raise
+        self._lib.lis_index_destroy(self._h)
+        self._h = new_h
+        self._cap = (cap_r, cap_p)
+
+    def tombstone(self, page: int) -> None:
+        """Hide page number ``page`` (position, not id) from all future searches (``lis_index_tombstone``)."""
+        with torch.cuda.device(self.device):
+            N.check(self._lib.lis_index_tombstone(self._h, int(page), _stream(self.device)))
+
     # -- persistence ------------------------------------------------------------------------------
-    _CHUNK_ROWS = 1 << 22   # 1 GiB of 16-bit rows per copy
+    FORMAT = "lis-index-v2"
 
     def page_tables(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         """(offsets int64 [n+1], ids int64 [n], clamp uint8 [n]) copied to the host."""
         st = self._as_store()
         ids = _wrap_device(self._lib.lis_index_ids(self._h), (len(self),), torch.int64, self.device)
-        return st.offsets.cpu().numpy(), ids.cpu().numpy(), st.clamp.cpu().numpy()
+        return (np.ascontiguousarray(st.offsets.cpu().numpy()), np.ascontiguousarray(ids.cpu().numpy()),
+                np.ascontiguousarray(st.clamp.cpu().numpy()))
 
-    def save(self, path) -> None:
-        """Write the index to a directory: ``meta.json``, raw row planes (``tokens.bin`` [+ ``tokens_lo.bin``]),
-        ``offsets.npy`` / ``ids.npy`` / ``clamp.npy`` and ``payloads.pkl``.  The row files are exactly the HBM
-        layout, so loading is a straight copy (memory-mapped, chunked) with no re-encoding."""
+    def _write_shard(self, d, p0: int, p1: int, off: np.ndarray, ids: np.ndarray, clamp: np.ndarray,
+                     io_threads: int = 0) -> dict:
+        """One shard directory: pages [p0, p1) of this index.  Row files are exactly the HBM layout."""
         import json
-        import pickle
-        from pathlib import Path
 
-        d = Path(path)
         d.mkdir(parents=True, exist_ok=True)
-        n, rows = len(self), self.num_rows
-        off, ids, clamp = self.page_tables() if n else (np.zeros(1, np.int64), np.zeros(0, np.int64), np.zeros(0, np.uint8))
-        np.save(d / "offsets.npy", off); np.save(d / "ids.npy", ids); np.save(d / "clamp.npy", clamp)
+        r0, r1 = int(off[p0]), int(off[p1])
+        np.save(d / "offsets.npy", off[p0:p1 + 1] - off[p0])
+        np.save(d / "ids.npy", ids[p0:p1])
+        np.save(d / "clamp.npy", clamp[p0:p1])
         planes = 2 if self.dtype == torch.float32 else 1
         with torch.cuda.device(self.device):
             for pl in range(planes):
-                with open(d / ("tokens_lo.bin" if pl else "tokens.bin"), "wb") as f:
-                    for r0 in range(0, rows, self._CHUNK_ROWS):
-                        nr = min(self._CHUNK_ROWS, rows - r0)
-                        buf = torch.empty((nr, N.DIM), dtype=torch.int16)
-                        N.check(self._lib.lis_index_read_plane(self._h, pl, r0, nr, buf.data_ptr(), _stream(self.device)))
-                        f.write(buf.numpy().tobytes())
-        with open(d / "payloads.pkl", "wb") as f:
-            pickle.dump(self.payloads, f)
-        (d / "meta.json").write_text(json.dumps({
-            "format": "lis-index-v1", "dtype": str(self.dtype).split(".")[-1], "n_pages": n, "n_rows": rows, "dim": N.DIM,
-            "planes": planes}))
+                f = d / ("tokens_lo.bin" if pl else "tokens.bin")
+                f.write_bytes(b"")
+                N.check(self._lib.lis_index_save_rows(self._h, pl, r0, r1 - r0, str(f).encode(), 0, io_threads,
+                                                      _stream(self.device)))
+        pays = {int(i): self.payloads[int(i)] for i in ids[p0:p1].tolist() if int(i) in self.payloads}
+        try:
+            (d / "payloads.json").write_text(json.dumps({str(k): v for k, v in pays.items()}))
+            payload_file = "payloads.json"
+        except (TypeError, ValueError):
+            import pickle
 
-    @classmethod
-    def load(cls, path, device=None, capacity_rows: Optional[int] = None, capacity_pages: Optional[int] = None
-             ) -> "LateInteractionIndex":
-        """Inverse of :meth:`save`; capacities default to the stored sizes (pass larger ones to keep adding)."""
+            with open(d / "payloads.pkl", "wb") as fh:
+                pickle.dump(pays, fh)
+            payload_file = "payloads.pkl"
+        return {"dir": d.name, "n_pages": p1 - p0, "n_rows": r1 - r0, "payloads": payload_file,
+                "id_min": int(ids[p0:p1].min()) if p1 > p0 else -1, "id_max": int(ids[p0:p1].max()) if p1 > p0 else -1}
+
+    def save(self, path, shards: int = 1, io_threads: int = 0) -> dict:
+        """Write the index as a sharded directory: ``manifest.json`` + ``shard-00000/ ...`` each holding the raw row
+        planes (``tokens.bin`` [+ ``tokens_lo.bin``], exactly as they sit in HBM), ``offsets.npy`` / ``ids.npy`` /
+        ``clamp.npy`` and the payloads (JSON when they are JSON-serialisable, else pickle).  ``shards``: how many
+        pieces of roughly equal token count to cut this index into (a later multi-GPU load maps shards to ranks
+        without touching the row files).  Rows leave the device through a pinned double buffer
+        (``lis_index_save_rows``).  Returns the manifest."""
         import json
-        import pickle
+        from pathlib import Path
+
+        from .sharded import balanced_shard_ranges
+
+        d = Path(path)
+        d.mkdir(parents=True, exist_ok=True)
+        n = len(self)
+        off, ids, clamp = self.page_tables() if n else (np.zeros(1, np.int64), np.zeros(0, np.int64), np.zeros(0, np.uint8))
+        ranges = balanced_shard_ranges(np.diff(off), max(1, min(int(shards), max(n, 1)))) if n else [(0, 0)]
+        entries = [self._write_shard(d / f"shard-{i:05d}", a, b, off, ids, clamp, io_threads) for i, (a, b) in enumerate(ranges)]
+        manifest = {"format": self.FORMAT, "dtype": str(self.dtype).split(".")[-1], "dim": N.DIM,
+                    "planes": 2 if self.dtype == torch.float32 else 1, "n_pages": n, "n_rows": self.num_rows,
+                    "row_bytes": 2 * N.DIM, "shards": entries}
+        (d / "manifest.json").write_text(json.dumps(manifest, indent=1))
+        return manifest
+
+    @staticmethod
+    def read_manifest(path) -> dict:
+        import json
         from pathlib import Path
 
         d = Path(path)
-        meta = json.loads((d / "meta.json").read_text())
-        if meta.get("format") != "lis-index-v1" or meta.get("dim") != N.DIM:
-            raise ValueError(f"{d} is not a lis-index-v1 directory")
-        dtype = getattr(torch, meta["dtype"])
-        n, rows = int(meta["n_pages"]), int(meta["n_rows"])
+        if (d / "manifest.json").exists():
+            m = json.loads((d / "manifest.json").read_text())
+            if m.get("format") != LateInteractionIndex.FORMAT or m.get("dim") != N.DIM:
+                raise ValueError(f"{d} is not a {LateInteractionIndex.FORMAT} directory")
+            return m
+        if (d / "meta.json").exists():      # round-1 layout: one unsharded directory
+            m = json.loads((d / "meta.json").read_text())
+            if m.get("format") != "lis-index-v1" or m.get("dim") != N.DIM:
+                raise ValueError(f"{d} is not a lis-index directory")
+            return {"format": LateInteractionIndex.FORMAT, "dtype": m["dtype"], "dim": N.DIM, "planes": m["planes"],
+                    "n_pages": m["n_pages"], "n_rows": m["n_rows"], "row_bytes": 2 * N.DIM,
+                    "shards": [{"dir": ".", "n_pages": m["n_pages"], "n_rows": m["n_rows"], "payloads": "payloads.pkl"}]}
+        raise ValueError(f"{d} holds no manifest.json")
+
+    @classmethod
+    def load(cls, path, device=None, capacity_rows: Optional[int] = None, capacity_pages: Optional[int] = None,
+             shard_ids: Optional[Sequence[int]] = None, allow_pickle: bool = False, io_threads: int = 0
+             ) -> "LateInteractionIndex":
+        """Inverse of :meth:`save`.  ``shard_ids``: which shards of the directory to load, in order (default: all) --
+        this is how a rank of a multi-GPU job picks its part (:meth:`ShardedIndex.load`).  Rows go from the files to
+        HBM through a pinned double buffer with parallel reads (``lis_index_load_rows``); capacities default to the
+        loaded sizes.  Pickled payloads are only read with ``allow_pickle=True`` (unpickling runs code: the directory
+        must be trusted); JSON payloads need no flag."""
+        import json
+        from pathlib import Path
+
+        d = Path(path)
+        man = cls.read_manifest(d)
+        dtype = getattr(torch, man["dtype"])
+        shards = man["shards"]
+        pick = list(range(len(shards))) if shard_ids is None else [int(i) for i in shard_ids]
+        rows = sum(int(shards[i]["n_rows"]) for i in pick)
+        n = sum(int(shards[i]["n_pages"]) for i in pick)
         idx = cls(max(capacity_rows or rows, rows, 1), max(capacity_pages or n, n, 1), dtype=dtype, device=device)
+        offs, idl, cll = [np.zeros(1, np.int64)], [], []
+        row0 = 0
         with torch.cuda.device(idx.device):
-            for pl in range(int(meta["planes"])):
-                if rows == 0:
-                    break
-                mm = np.memmap(d / ("tokens_lo.bin" if pl else "tokens.bin"), dtype=np.int16, mode="r", shape=(rows, N.DIM))
-                for r0 in range(0, rows, cls._CHUNK_ROWS):
-                    nr = min(cls._CHUNK_ROWS, rows - r0)
-                    chunk = np.ascontiguousarray(mm[r0:r0 + nr])
-                    N.check(idx._lib.lis_index_write_rows(idx._h, pl, r0, nr, chunk.ctypes.data, _stream(idx.device)))
-            off = np.ascontiguousarray(np.load(d / "offsets.npy"), dtype=np.int64)
-            ids = np.ascontiguousarray(np.load(d / "ids.npy"), dtype=np.int64)
-            clamp = np.ascontiguousarray(np.load(d / "clamp.npy"), dtype=np.uint8)
-            if len(off) != n + 1 or len(ids) != n or len(clamp) != n or (n and off[-1] != rows):
-                raise ValueError(f"{d}: page tables are inconsistent with meta.json")
-            N.check(idx._lib.lis_index_set_tables(idx._h, off.ctypes.data, ids.ctypes.data if n else None,
-                                                  clamp.ctypes.data if n else None, n, _stream(idx.device)) if n else 0)
-        with open(d / "payloads.pkl", "rb") as f:
-            idx.payloads = pickle.load(f)
+            for i in pick:
+                sd = d / shards[i]["dir"]
+                nr = int(shards[i]["n_rows"])
+                for pl in range(int(man["planes"])):
+                    f = sd / ("tokens_lo.bin" if pl else "tokens.bin")
+                    if nr and f.stat().st_size != nr * 2 * N.DIM:
+                        raise ValueError(f"{f}: size does not match the manifest")
+                    N.check(idx._lib.lis_index_load_rows(idx._h, pl, row0, nr, str(f).encode(), 0, io_threads,
+                                                         _stream(idx.device)))
+                off = np.load(sd / "offsets.npy").astype(np.int64)
+                if len(off) != int(shards[i]["n_pages"]) + 1 or off[0] != 0 or off[-1] != nr:
+                    raise ValueError(f"{sd}: page tables are inconsistent with the manifest")
+                offs.append(off[1:] + row0)
+                idl.append(np.load(sd / "ids.npy").astype(np.int64))
+                cll.append(np.load(sd / "clamp.npy").astype(np.uint8))
+                row0 += nr
+                pf = shards[i].get("payloads", "payloads.json")
+                if pf.endswith(".json") and (sd / pf).exists():
+                    idx.payloads.update({int(k): v for k, v in json.loads((sd / pf).read_text()).items()})
+                elif (sd / pf).exists():
+                    if not allow_pickle:
+                        raise ValueError(f"{sd / pf} is a pickle; pass allow_pickle=True only for directories you trust")
+                    import pickle
+
+                    with open(sd / pf, "rb") as fh:
+                        idx.payloads.update(pickle.load(fh))
+            if n:
+                off = np.ascontiguousarray(np.concatenate(offs))
+                ids = np.ascontiguousarray(np.concatenate(idl))
+                clamp = np.ascontiguousarray(np.concatenate(cll))
+                N.check(idx._lib.lis_index_set_tables(idx._h, off.ctypes.data, ids.ctypes.data, clamp.ctypes.data, n,
+                                                      _stream(idx.device)))
         return idx
 
     # -- search -----------------------------------------------------------------------------------
@@ -249,15 +392,44 @@ class LateInteractionIndex:
             N.check(self._lib.lis_index_search(self._h, pq.rows.data_ptr(),
                                                None if pq.rows_lo is None else pq.rows_lo.data_ptr(),
                                                pq.rows.shape[0], seg_lo, seg_hi, mt_seg,
-                                               plan.n_seg, plan.n_mtiles, seg_first, plan.nq, _ROUND[round_mode],
+                                               plan.n_seg, plan.n_mtiles, None if plan.direct else seg_first, plan.nq,
+                                               _ROUND[round_mode],
                                                int(k), out_s.data_ptr(), out_i.data_ptr(), _stream(self.device)))
         return out_s, out_i
 
-    def search(self, qs: TensorOrList, k: int, round_mode: str = "f32") -> Tuple[torch.Tensor, torch.Tensor]:
+    def search(self, qs: TensorOrList, k: int, round_mode: str = "f32", comm=None) -> Tuple[torch.Tensor, torch.Tensor]:
         """Host-facing search: (scores fp32 [nq,k], page ids int64 [nq,k]) on the CPU, best first,
-        ties broken by ascending id; slots beyond the corpus size hold (-inf, -1)."""
-        s, i = self.search_device(qs, k, round_mode)
-        return s.cpu(), i.cpu()
+        ties broken by ascending id; slots beyond the corpus size hold (-inf, -1).
+
+        One C call (``lis_index_search_sharded``): queries are packed on the host, and the whole device sequence
+        -- upload, K1, segment sums, K2, [all-gather + merge when ``comm`` spans several ranks,] download -- replays
+        as one CUDA graph per query shape.  ``comm``: a ``lis_comm`` handle (see :class:`ShardedIndex`)."""
+        if len(qs) == 0:
+            raise ValueError("No queries provided")
+        if comm is None and len(self) == 0:
+            raise ValueError("No passages provided")
+        if round_mode not in _ROUND:
+            raise ValueError(f"round_mode must be one of {sorted(_ROUND)}")
+        k = int(k)
+        rows, lens = _flatten_queries(qs, self.dtype)
+        plan = plan_queries(lens)
+        if plan.n_seg == 0:
+            raise ValueError("No queries provided")
+        out_s = torch.empty((plan.nq, k), dtype=torch.float32)
+        out_i = torch.empty((plan.nq, k), dtype=torch.int64)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.lis_index_search_sharded(
+                self._h, comm, rows.data_ptr(), rows.shape[0], plan.seg_lo.ctypes.data, plan.seg_hi.ctypes.data,
+                plan.mt_seg.ctypes.data, plan.n_seg, plan.n_mtiles, None if plan.direct else plan.seg_first.ctypes.data,
+                plan.nq, _ROUND[round_mode], k, out_s.data_ptr(), out_i.data_ptr(),
+                _stream(self.device) if rows.is_cuda else None))
+        return out_s, out_i
+
+    def graph_stats(self) -> Tuple[int, int, int]:
+        """(cached search graphs, captures, replays) of the one-shot search path."""
+        cap, rep = C.c_int64(0), C.c_int64(0)
+        n = self._lib.lis_index_graph_stats(self._h, C.byref(cap), C.byref(rep))
+        return int(n), int(cap.value), int(rep.value)
 
     def scores(self, qs: TensorOrList, round_mode: str = "f32") -> torch.Tensor:
         """Full device fp32 ``[nq, n_pages]`` score matrix against the resident corpus."""
@@ -280,6 +452,26 @@ class LateInteractionIndex:
         if self.dtype == torch.float32:
             lo = _wrap_device(self._lib.lis_index_tokens_lo(self._h), (rows, N.DIM), plane, self.device)
         return PageStore(tok, off, cl, n, lo, self.dtype)
+
+
+def _flatten_queries(qs: TensorOrList, dtype: torch.dtype) -> Tuple[torch.Tensor, Tuple[int, ...]]:
+    """Queries as ONE contiguous ``[rows, 128]`` matrix of the index dtype, where they already live (host
+    tensors stay on the host: the C call uploads them together with the segment tables), plus their lengths."""
+    if isinstance(qs, torch.Tensor) and qs.dim() == 3:
+        nq, n_tok, d = qs.shape
+        if d != N.DIM:
+            raise ValueError(f"queries: embedding width {d} != {N.DIM}")
+        flat, lens = qs.reshape(nq * n_tok, d), (n_tok,) * nq
+    else:
+        ql = _as_list(qs)
+        for t in ql:
+            _check_rows(t, "query")
+        lens = tuple(int(t.shape[0]) for t in ql)
+        if len({t.device for t in ql}) > 1:
+            ql = [t.cpu() for t in ql]
+        flat = ql[0] if len(ql) == 1 else torch.cat(ql, dim=0)
+    flat = flat.detach().to(dtype).contiguous()
+    return flat, lens
 
 
 class _CudaArrayView:

@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import time
 import uuid
-import weakref
+from collections import OrderedDict
 from dataclasses import dataclass, field
 from typing import Any, Dict, Iterable, List, Optional, Sequence
 
@@ -30,7 +30,8 @@ VECTOR_SIZE = N.DIM  # 01_create_context_qdrant.py:70
 # ------------------------------------------------------------------------------------------------
 # score_results
 # ------------------------------------------------------------------------------------------------
-_DATASET_INDEX: Dict[int, Any] = {}
+_DATASET_INDEX: "OrderedDict[int, tuple]" = OrderedDict()   # id(dataset) -> (fingerprint, index); LRU, bounded
+_DATASET_CACHE_MAX = 4
 
 
 def _embeddings_of(outputs: Any) -> torch.Tensor:
@@ -39,26 +40,52 @@ def _embeddings_of(outputs: Any) -> torch.Tensor:
     return outputs.embeddings if hasattr(outputs, "embeddings") else outputs
 
 
+def _dataset_fingerprint(dataset: Sequence[dict]) -> tuple:
+    """Cheap content check: length plus storage address, shape and version counter of a few embeddings -- replacing
+    or editing entries in place (same list object, same length) changes it."""
+    n = len(dataset)
+    probe = sorted({0, n // 3, n // 2, (2 * n) // 3, n - 1}) if n else []
+    out = [n]
+    for i in probe:
+        e = dataset[i]["embedding"]
+        out.append((e.data_ptr(), tuple(e.shape), str(e.dtype), getattr(e, "_version", 0)))
+    return tuple(out)
+
+
+def invalidate_dataset_index(dataset: Optional[Sequence[dict]] = None) -> None:
+    """Drop the cached GPU index of ``dataset`` (or of every dataset) and release its HBM."""
+    keys = list(_DATASET_INDEX) if dataset is None else [id(dataset)]
+    for k in keys:
+        hit = _DATASET_INDEX.pop(k, None)
+        if hit is not None:
+            hit[1].close()
+
+
 def index_for_dataset(dataset: Sequence[dict], device=None, dtype: Optional[torch.dtype] = None) -> LateInteractionIndex:
     """Build (once per dataset object) the GPU index over ``entry["embedding"]`` -- this replaces the
-    ``torch.stack`` of the whole corpus that the reference repeats on every call (05_experiment02.py:213)."""
-    key = id(dataset)
-    hit = _DATASET_INDEX.get(key)
-    if hit is not None and hit[0]() is dataset and hit[1] == len(dataset):
-        return hit[2]
+    ``torch.stack`` of the whole corpus that the reference repeats on every call (05_experiment02.py:213).
+    The cache holds no reference to the dataset, is validated by a content fingerprint, keeps at most
+    ``_DATASET_CACHE_MAX`` indexes (least recently used ones are closed) and can be emptied with
+    :func:`invalidate_dataset_index`."""
     if len(dataset) == 0:
         raise ValueError("No passages provided")
+    key = id(dataset)
+    fp = _dataset_fingerprint(dataset)
+    hit = _DATASET_INDEX.get(key)
+    if hit is not None:
+        if hit[0] == fp:
+            _DATASET_INDEX.move_to_end(key)
+            return hit[1]
+        _DATASET_INDEX.pop(key)[1].close()       # same object, different content (or a recycled id)
     embs = [entry["embedding"] for entry in dataset]
     dt = dtype or (embs[0].dtype if embs[0].dtype in (torch.bfloat16, torch.float16, torch.float32) else torch.bfloat16)
     rows = sum(int(e.shape[0]) for e in embs)
-    idx = LateInteractionIndex(rows, len(embs), dtype=dt, device=device)
+    idx = LateInteractionIndex(max(rows, 1), len(embs), dtype=dt, device=device)
     # torch.stack in the reference implies equal lengths; ragged lists get pad_sequence semantics
     idx.add(embs, zero_pad_block=128)
-    try:
-        ref = weakref.ref(dataset)
-    except TypeError:  # plain lists are not weak-referenceable
-        ref = (lambda d=dataset: d)
-    _DATASET_INDEX[key] = (ref, len(dataset), idx)
+    _DATASET_INDEX[key] = (fp, idx)
+    while len(_DATASET_INDEX) > _DATASET_CACHE_MAX:
+        _DATASET_INDEX.popitem(last=False)[1][1].close()
     return idx
 
 
@@ -73,6 +100,25 @@ def load_embedding_cache(path: str) -> List[dict]:
     if not isinstance(dataset, list) or (dataset and "embedding" not in dataset[0]):
         raise ValueError(f"{path} is not a page-embedding cache (list of dicts with an 'embedding' entry)")
     return dataset
+
+
+def convert_embedding_cache(pkl_path: str, out_dir: str, shards: int = 1, device=None,
+                            dtype: Optional[torch.dtype] = None) -> dict:
+    """Turn the reference's pickle cache (05_experiment02.py:391-398) into the sharded on-disk index format
+    (``LateInteractionIndex.save``): page id = position in the list, payload = ``{doc_id, page_id, file_name}``.
+    ``shards``: pieces of equal token count, e.g. the number of GPUs that will serve it.  Returns the manifest."""
+    dataset = load_embedding_cache(pkl_path)
+    if not dataset:
+        raise ValueError("No passages provided")
+    embs = [e["embedding"] for e in dataset]
+    dt = dtype or (embs[0].dtype if embs[0].dtype in (torch.bfloat16, torch.float16, torch.float32) else torch.bfloat16)
+    idx = LateInteractionIndex(max(sum(int(e.shape[0]) for e in embs), 1), len(embs), dtype=dt, device=device)
+    try:
+        idx.add(embs, zero_pad_block=128,
+                payloads=[{k: e[k] for k in ("doc_id", "page_id", "file_name") if k in e} for e in dataset])
+        return idx.save(out_dir, shards=shards)
+    finally:
+        idx.close()
 
 
 def create_document_embeddings(images_per_pdf: dict, model, processor, batch_size: int = 2) -> List[dict]:
@@ -112,9 +158,14 @@ def colpali_qdrant(dataset, papers, doi, model, processor, qdrant_client, qdrant
                 payload={"document_name": batch[j]["filename"], "document_id": str(uuid.uuid4()),
                          "document_link": links[0] if links else "", "type": "pdf_page", "page_no": batch[j]["page_no"],
                          "ref": "", "caption": "", "img_link": batch[j]["img_link"]}))
+        if direct:
+            # the in-process index has no transient failures to ride out: an error here (bad vectors, HBM exhausted)
+            # would silently lose pages if it were swallowed, so it propagates
+            qdrant_client.upsert(collection_name=qdrant_collection, points=points)
+            continue
         try:
             qdrant_client.upsert(collection_name=qdrant_collection, points=points)
-        except Exception as e:  # the reference skips the batch and carries on (functions.py:866-868)
+        except Exception as e:  # a remote Qdrant: the reference skips the batch and carries on (functions.py:866-868)
             print(f"Error during upsert: {e}")
             continue
     print("Indexing complete!")
@@ -176,8 +227,9 @@ class PointStruct:
 @dataclass
 class _Collection:
     index: LateInteractionIndex
-    point_ids: List[Any]
+    point_ids: List[Any]                     # per stored page (position): the caller's point id
     payloads: List[Optional[dict]]
+    live: Dict[Any, int] = field(default_factory=dict)   # point id -> position of its current version
     filter_cache: Dict[Any, torch.Tensor] = field(default_factory=dict)
 
 
@@ -204,8 +256,12 @@ def _filter_conditions(query_filter: Any) -> List[tuple]:
 class MaxSimClient:
     """In-process stand-in for the Qdrant server on the multivector MAX_SIM route."""
 
-    def __init__(self, device=None, dtype: torch.dtype = torch.bfloat16, capacity_rows: int = 4_000_000,
-                 capacity_pages: int = 8192):
+    def __init__(self, device=None, dtype: torch.dtype = torch.float32, capacity_rows: int = 1_000_000,
+                 capacity_pages: int = 2048):
+        """``dtype``: storage of the vectors.  float32 (default) is what Qdrant stores for this collection
+        (SURVEY a4/a5: no quantisation configured) and is scored as two bf16 planes with fp32 accumulation;
+        ``torch.bfloat16`` halves HBM and doubles throughput at ~1e-2 score error.  The capacities are only the
+        initial allocation: the store grows (doubling) when an upsert does not fit."""
         self.device = resolve_device(device)
         self.dtype = dtype
         self.capacity_rows = capacity_rows
@@ -240,7 +296,7 @@ class MaxSimClient:
         return col is not None
 
     def count(self, collection_name: str) -> int:
-        return len(self._collections[collection_name].index)
+        return len(self._collections[collection_name].live)
 
     # -- ingestion --------------------------------------------------------------------------------
     def upsert(self, collection_name: str, points: Iterable[Any], **_: Any) -> None:
@@ -262,8 +318,24 @@ class MaxSimClient:
             pays.append(pay)
         if not pages:
             return
+        # a point id seen twice in one call: the last version wins, like consecutive upserts
+        last = {pid: j for j, pid in enumerate(pids)}
+        keep = sorted(last.values())
+        pages, pids, pays = [pages[j] for j in keep], [pids[j] for j in keep], [pays[j] for j in keep]
+        idx = col.index
+        need_rows = idx.num_rows + sum(int(p.shape[0]) for p in pages)
+        need_pages = len(idx) + len(pages)
+        cap_rows, cap_pages = idx.capacity
+        if need_rows > cap_rows or need_pages > cap_pages:      # grow instead of dropping pages
+            idx.reserve(max(need_rows, 2 * cap_rows) if need_rows > cap_rows else cap_rows,
+                        max(need_pages, 2 * cap_pages) if need_pages > cap_pages else cap_pages)
         base = len(col.point_ids)
-        col.index.add(pages, ids=list(range(base, base + len(pages))))
+        idx.add(pages, ids=list(range(base, base + len(pages))))
+        for j, pid in enumerate(pids):          # upsert semantics: the new version replaces the old one
+            old = col.live.get(pid)
+            if old is not None:
+                idx.tombstone(old)
+            col.live[pid] = base + j
         col.point_ids.extend(pids)
         col.payloads.extend(pays)
         col.filter_cache.clear()
@@ -281,7 +353,7 @@ class MaxSimClient:
             raise ValueError(f"query must be [n_tok, {VECTOR_SIZE}], got {tuple(q.shape)}")
         nrm = q.norm(dim=-1, keepdim=True)
         q = torch.where(nrm > 0, q / nrm.clamp_min(1e-30), q).to(self.dtype)
-        k = max(1, min(int(limit), len(col.index), N.MAX_K))
+        k = max(1, min(int(limit), len(col.live), N.MAX_K))
         conds = _filter_conditions(query_filter)
         if not conds:
             scores, ids = col.index.search([q], k)
@@ -289,7 +361,9 @@ class MaxSimClient:
             key = tuple(conds)
             masked = col.filter_cache.get(key)
             if masked is None:
-                keep = np.asarray([
+                current = np.zeros(len(col.payloads), dtype=bool)
+                current[list(col.live.values())] = True          # replaced versions never match
+                keep = current & np.asarray([
                     all(((pay or {}).get("metadata", pay or {}).get(kk) == vv) or ((pay or {}).get(kk) == vv)
                         for kk, vv in conds)
                     for pay in col.payloads], dtype=bool)

@@ -62,8 +62,10 @@ class QueryPlan:
 
     @property
     def direct(self) -> bool:
-        """True when no query was cut: K1's output rows are the per-query scores."""
-        return self.n_seg == self.nq
+        """True when K1's output rows are the per-query scores: segment s belongs to query s, i.e. no query was
+        cut and none is empty (an empty query owns no segment, so the counts alone cannot tell: lens [0, 100] give
+        two segments of query 1)."""
+        return self.n_seg == self.nq and bool((self.seg_query == np.arange(self.nq, dtype=np.int32)).all())
 
 
 def plan_queries(q_lens: Sequence[int]) -> QueryPlan:
@@ -291,6 +293,64 @@ def maxsim_scores_device(pq: PackedQueries, store: PageStore, round_mode: str = 
     return out
 
 
+def _host_corpus(ps: TensorOrList) -> bool:
+    if isinstance(ps, torch.Tensor):
+        return ps.device.type == "cpu" and ps.dim() == 3
+    return len(ps) > 0 and all(isinstance(t, torch.Tensor) and t.device.type == "cpu" for t in ps)
+
+
+def stream_scores_host_corpus(pq: PackedQueries, ps: TensorOrList, batch_size: int, round_mode: str,
+                              chunk_rows: int = 0, host_threads: int = 0) -> torch.Tensor:
+    """K1 over a corpus that stays in HOST memory (``lis_stream_scores``): chunks of whole pages go through a pinned
+    double buffer on a copy stream while the previous chunk is being scored -- no ``torch.cat`` / ``torch.stack`` of the
+    corpus (05_experiment02.py:213 does one per call) and no need for the corpus to fit HBM.  16-bit embeddings;
+    ``ps`` is a CPU ``[n, S, 128]`` tensor or a list of per-page CPU tensors.  Returns device fp32 ``[nq, np]``."""
+    lib = N.load()
+    device = pq.rows.device
+    plan = pq.plan
+    keep = None
+    if isinstance(ps, torch.Tensor):
+        n, s_len, d = ps.shape
+        if d != N.DIM:
+            raise ValueError(f"passages: embedding width {d} != {N.DIM}")
+        flat = ps.detach().contiguous()
+        lens = np.full(n, s_len, dtype=np.int64)
+        tok_ptr, ptrs, keep = flat.data_ptr(), None, flat
+    else:
+        pl = list(ps)
+        for t in pl:
+            _check_rows(t, "passage")
+        _common_dtype(pl, "passages")
+        pl = [t.detach() if t.is_contiguous() else t.detach().contiguous() for t in pl]
+        lens = np.asarray([int(t.shape[0]) for t in pl], dtype=np.int64)
+        ptrs = np.asarray([t.data_ptr() for t in pl], dtype=np.uint64)
+        tok_ptr, keep = None, pl
+        n = len(pl)
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    n_rows = int(offsets[-1])
+    if n_rows == 0:
+        raise ValueError("No passages provided")
+    flags = None if isinstance(ps, torch.Tensor) else clamp_flags(lens, batch_size)
+    if flags is not None and not flags.any():
+        flags = None
+    seg_lo, seg_hi, mt_seg, seg_first = pq.table_ptrs()
+    direct = plan.direct
+    rm = _ROUND[round_mode]
+    out = torch.empty((plan.nq, n), dtype=torch.float32, device=device)
+    seg_out = out if direct else torch.empty((plan.n_seg, n), dtype=torch.float32, device=device)
+    st = _stream(device)
+    N.check(lib.lis_stream_scores(pq.rows.data_ptr(), pq.rows.shape[0], seg_lo, seg_hi, mt_seg, plan.n_seg, plan.n_mtiles,
+                                  tok_ptr, None if ptrs is None else ptrs.ctypes.data, n_rows, offsets.ctypes.data,
+                                  None if flags is None else flags.ctypes.data, n, _DTYPES[pq.dtype],
+                                  rm if direct else rm | N.ROUND_DEFER_SUM, seg_out.data_ptr(), seg_out.stride(0),
+                                  int(chunk_rows), int(host_threads), st))
+    del keep
+    if not direct:
+        N.check(lib.lis_reduce_segments(seg_out.data_ptr(), seg_out.stride(0), seg_first, plan.nq, n, rm,
+                                        _DTYPES[pq.dtype], out.data_ptr(), out.stride(0), st))
+    return out
+
+
 def score_multi_vector(qs: TensorOrList, ps: TensorOrList, batch_size: int = 128,
                        device: Union[str, torch.device, None] = None, *, round_mode: str = "reference",
                        return_device: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -320,10 +380,16 @@ def score_multi_vector(qs: TensorOrList, ps: TensorOrList, batch_size: int = 128
     N.check(N.load().lis_device_supported(dev.index))
     with torch.cuda.device(dev):
         pq = pack_queries(qs, dev)
-        store = build_page_store(ps, dev, pq.dtype, batch_size)
-        if store.n_rows == 0:
-            raise ValueError("No passages provided")
-        scores = maxsim_scores_device(pq, store, round_mode)
+        if round_mode not in _ROUND:
+            raise ValueError(f"round_mode must be one of {sorted(_ROUND)}")
+        if pq.dtype in _DTYPES and _host_corpus(ps):
+            # the reference's literal call: the corpus is a CPU tensor / list (05_experiment02.py:213-214)
+            scores = stream_scores_host_corpus(pq, ps, batch_size, round_mode)
+        else:
+            store = build_page_store(ps, dev, pq.dtype, batch_size)
+            if store.n_rows == 0:
+                raise ValueError("No passages provided")
+            scores = maxsim_scores_device(pq, store, round_mode)
         if return_device:
             return scores
         if out is not None:

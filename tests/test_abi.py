@@ -30,7 +30,7 @@ def test_header_symbols_exported_and_bound(native):
         assert hasattr(lib, n), f"liblis.so does not export {n}"
         assert n in native.SIGNATURES, f"_native.py does not bind {n}"
     assert set(native.SIGNATURES) == set(names)
-    assert lib.lis_abi_version() == 1
+    assert lib.lis_abi_version() == 2
 
 
 def test_no_torch_types_in_abi():
@@ -53,7 +53,8 @@ def ref_plan(lens):
     return segs, (row + 127) // 128
 
 
-@pytest.mark.parametrize("lens", [[16], [20] * 32, [32] * 1024, [100, 100, 300, 0, 5], [128, 128], [1] * 300, [0, 0, 7]])
+@pytest.mark.parametrize("lens", [[16], [20] * 32, [32] * 1024, [100, 100, 300, 0, 5], [128, 128], [1] * 300, [0, 0, 7],
+                                  [0, 100], [0, 30], [30, 0], [64, 0, 64]])
 def test_plan_queries(lis, lens):
     plan = lis.plan_queries(lens)
     segs, tiles = ref_plan(lens)
@@ -67,7 +68,8 @@ def test_plan_queries(lis, lens):
     for q in range(len(lens)):
         mine = list(range(plan.seg_first[q], plan.seg_first[q + 1]))
         assert sum(plan.seg_hi[s] - plan.seg_lo[s] for s in mine) == lens[q]
-    assert plan.direct == (len(segs) == len(lens))
+    # direct == segment s IS query s: nothing cut and nothing empty (lens [0, 100] give 2 segments for 2 queries)
+    assert plan.direct == (len(segs) == len(lens) and all(n > 0 for n in lens))
 
 
 def test_plan_queries_errors(native):
@@ -97,6 +99,22 @@ def test_argument_validation_without_gpu(native):
     assert "null pointer" in native.last_error()
     assert lib.lis_topk(None, 0, 1, 1, None, 0, 5000, None, None, None, 0, None) == native.LIS_E_INVALID
     assert lib.lis_index_num_pages(None) == 0
+
+
+def test_new_entry_points_validate_without_gpu(native):
+    """ABI v2 additions: argument validation happens before any CUDA call."""
+    lib = native.load()
+    assert lib.lis_index_search_sharded(None, None, None, 0, None, None, None, 0, 0, None, 0, 0, 1, None, None, None) \
+        == native.LIS_E_INVALID
+    assert lib.lis_comm_unique_id(None, 0) == native.LIS_E_INVALID
+    assert lib.lis_comm_rank(None) == 0 and lib.lis_comm_world(None) == 1
+    assert lib.lis_stream_scores(None, 0, None, None, None, 0, 0, None, None, 0, None, None, 0, 0, 0, None, 0, 0, 0, None) \
+        == native.LIS_E_INVALID
+    assert lib.lis_index_add_projected(None, None, 0, 0, 0, None, None, None, 1, 0, None, None) == native.LIS_E_INVALID
+    assert lib.lis_project_normalize(None, 1, 64, None, None, None, 0, 0, 7, None, None, None) == native.LIS_E_INVALID
+    assert "round_mode" in native.last_error()
+    assert lib.lis_nccl_version() >= 0
+    lib.lis_stream_release()
 
 
 def test_topk_workspace_sizes(native):
