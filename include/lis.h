@@ -133,7 +133,7 @@ int lis_reduce_segments(const float* seg_scores, int64_t ld_seg, const int32_t* 
 
 /* Tuning / debug knobs (process-wide); 0 always means "auto", and the defaults are what ships.
  *   tile_n     {0, 128, 192, 256}  page-token rows per MMA tile
- *   group      {0, 1..10}          most query M tiles resident per pass over the page store (4..6, 8, 10: CTA pairs only)
+ *   group      {0, 1..10}          most query M tiles resident per pass over the page store (4..10: CTA pairs only)
  *   max_ctas   0 = one per SM
  *   epi_halves {0, 1, 2}           4 or 8 epilogue warps
  *   a_operand  {0, 1, 2, 3}        query operand of the MMA in shared memory (1) or tensor memory (2) on one

@@ -6,9 +6,12 @@ searches that are in flight -- e.g. the per-question ``RetrievalManager.fetch`` 
 02_experiment01.py:141-164, or the asyncio fan-out of 05_experiment02.py:297-298 -- into one pass,
 multiplying queries/s at unchanged per-pass latency.
 
-Results are those of ``index.search([query], k)`` bit for bit: K1 scores every (query, page) pair
-independently of what else shares the pass, and the top-``k`` prefix of a top-``kmax`` list under the total
-order (score desc, id asc) is the top-``k`` list.
+Results are those of ``index.search([query], k)`` bit for bit: K1 scores every (query, page) pair independently
+of what else shares the pass -- the per-token maxima are exact, and the sum over a query's tokens follows one
+canonical order per segment (``reduce_tile_segments``) -- provided the query is cut into the same segments as when it
+is searched alone.  Segments are cut at multiples of 64 packed rows, so the batcher places every query where it
+crosses none (or, for a query longer than 64 tokens, where it starts on one), padding with zero rows when needed.
+The top-``k`` prefix of a top-``kmax`` list under the total order (score desc, id asc) is the top-``k`` list.
 """
 from __future__ import annotations
 
@@ -84,11 +87,30 @@ class QueryBatcher:
     def __exit__(self, *exc):
         self.close()
 
+    _CUT = 64      # lis_plan_queries cuts segments at multiples of 64 packed rows
+
+    @classmethod
+    def _placed_rows(cls, rows: int, n_tok: int) -> int:
+        """Packed rows in use after appending a query of ``n_tok`` tokens behind ``rows`` rows, padding included."""
+        room = cls._CUT - rows % cls._CUT
+        if rows % cls._CUT and (n_tok > room):
+            rows += room           # start on the next cut: the segments then equal those of the query searched alone
+        return rows + n_tok
+
     def _serve(self, batch: List) -> None:
         try:
             kmax = max(b[1] for b in batch)
-            scores, ids = self.index.search([b[0] for b in batch], kmax, self.round_mode)
-            for i, (_, k, fut) in enumerate(batch):
+            qs, where, rows = [], [], 0
+            for q, _, _ in batch:
+                room = self._CUT - rows % self._CUT
+                if rows % self._CUT and q.shape[0] > room:
+                    qs.append(torch.zeros((room, N.DIM), dtype=q.dtype, device=q.device))   # filler query, result ignored
+                    rows += room
+                where.append(len(qs))
+                qs.append(q)
+                rows += q.shape[0]
+            scores, ids = self.index.search(qs, kmax, self.round_mode)
+            for (_, k, fut), i in zip(batch, where):
                 fut.set_result((scores[i, :k].clone(), ids[i, :k].clone()))
         except BaseException as exc:
             if len(batch) == 1:
@@ -109,7 +131,7 @@ class QueryBatcher:
             if item is None:
                 break                        # the sentinel is the last thing ever queued (submit refuses after close)
             batch: List = [item]
-            rows = item[0].shape[0]
+            rows = item[0].shape[0]       # packed rows incl. the padding that keeps queries off the 64-row cuts
             deadline = time.perf_counter() + self.max_wait
             while rows < self.max_rows:
                 left = deadline - time.perf_counter()
@@ -122,9 +144,9 @@ class QueryBatcher:
                     pending = None
                     self._q.put(None)        # keep the sentinel at the tail; nothing can follow it
                     break
-                if rows + nxt[0].shape[0] > self.max_rows:
+                if self._placed_rows(rows, nxt[0].shape[0]) > self.max_rows:
                     pending = nxt            # keeps its place in the order of arrival
                     break
                 batch.append(nxt)
-                rows += nxt[0].shape[0]
+                rows = self._placed_rows(rows, nxt[0].shape[0])
             self._serve(batch)

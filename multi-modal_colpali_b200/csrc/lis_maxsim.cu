@@ -195,7 +195,7 @@ int lis_set_tuning(int tile_n, int group, int max_ctas, int epi_halves, int a_op
   LIS_REQUIRE(max_ctas >= 0, "max_ctas must be >= 0");
   LIS_REQUIRE(group >= 0 && group <= 10, "group must be in 0..10");
   LIS_REQUIRE(a_operand == 3 || (a_operand == 0 && tile_n == 0) || group <= 5, "group > 5 needs the CTA-pair form");
-  LIS_REQUIRE(a_operand != 3 || group == 0 || group >= 2, "the CTA-pair form keeps 2..6, 8 or 10 query tiles per pass");
+  LIS_REQUIRE(a_operand != 3 || group == 0 || group >= 2, "the CTA-pair form keeps 2..10 query tiles per pass");
   LIS_REQUIRE(a_operand != 3 || tile_n == 0 || tile_n == 256, "the CTA-pair form uses 256-row page tiles");
   if (tile_n && a_operand && a_operand != 3) {
     const int gm = max_group(tile_n, a_operand == 2);
@@ -341,15 +341,9 @@ static void build_pass_plan(const Tuning& tn, int64_t n_mtiles, bool must_single
     // experiments: CTA pairs only, balanced passes of at most `group` tiles (a leftover single tile runs on one CTA)
     const int gmax = tn.group ? std::min(std::max(tn.group, 2), 10) : 6;
     const int64_t passes = (n_mtiles + gmax - 1) / gmax;
-    int gp = (int)((n_mtiles + passes - 1) / passes);
-    if (gp == 7 || gp == 9) ++gp;                       // 7 and 9 resident tiles are not instantiated
+    const int gp = (int)((n_mtiles + passes - 1) / passes);
     for (int64_t t = 0; t < n_mtiles; t += gp) {
-      int n = (int)std::min<int64_t>(gp, n_mtiles - t);
-      if (n == 7 || n == 9) {                           // leftover of 7 / 9: 6 + 1 / 6 + 3
-        plan.push_back({true, 6});
-        t += 6 - gp;                                    // (the loop adds gp)
-        continue;
-      }
+      const int n = (int)std::min<int64_t>(gp, n_mtiles - t);
       plan.push_back({n >= 2, n});
     }
   } else {
@@ -358,7 +352,7 @@ static void build_pass_plan(const Tuning& tn, int64_t n_mtiles, bool must_single
     // One CTA per SM wins up to 3 tiles (a single tile is HBM-bound); CTA pairs win from 4 tiles on,
     // even tile counts being the efficient ones (no split tile); 8 and 10 tiles amortise the page stream a little more.
     static const float cost_single[4] = {0.f, 2.65f, 4.00f, 5.28f};
-    static const float cost_pair[11] = {0.f, 0.f, 4.05f, 5.73f, 6.58f, 8.83f, 9.30f, 0.f, 12.33f, 0.f, 15.20f};   // 0 = not instantiated
+    static const float cost_pair[11] = {0.f, 0.f, 4.05f, 5.73f, 6.58f, 8.83f, 9.30f, 11.9f, 12.33f, 14.9f, 15.20f};
     const int gcap = tn.group ? tn.group : 10;    // group = most tiles a pass may hold
     std::vector<float> best((size_t)n_mtiles + 1, 1e30f);
     std::vector<int8_t> choice((size_t)n_mtiles + 1, 0);       // +n = single pass of n tiles, -n = pair pass

@@ -47,7 +47,7 @@ static int launch_pair(const CUtensorMap& q, const CUtensorMap& p, const MaxSimA
   return LIS_OK;
 }
 
-// n_mt query M tiles (2..6, 8 or 10) in one pass: n_mt / 2 uses with M = 256 and, when n_mt is odd, one with M = 128.
+// n_mt query M tiles (2..10) in one pass: n_mt / 2 uses with M = 256 and, when n_mt is odd, one with M = 128.
 // q, p: tensor maps of the packed query rows and of the token store, both with 64-row boxes.
 int dispatch_maxsim_pair(const CUtensorMap& q, const CUtensorMap& p, const MaxSimArgs& a, int grid, cudaStream_t st,
                          bool dbg) {
@@ -68,10 +68,12 @@ int dispatch_maxsim_pair(const CUtensorMap& q, const CUtensorMap& p, const MaxSi
   LIS_PAIR_CASE(4, 2, false)
   LIS_PAIR_CASE(5, 2, true)
   LIS_PAIR_CASE(6, 3, false)
+  LIS_PAIR_CASE(7, 3, true)
   LIS_PAIR_CASE(8, 4, false)
+  LIS_PAIR_CASE(9, 4, true)
   LIS_PAIR_CASE(10, 5, false)
 #undef LIS_PAIR_CASE
-  set_error("pair kernel: unsupported tile count %d (2..6, 8, 10)", a.n_mt);
+  set_error("pair kernel: unsupported tile count %d (2..10)", a.n_mt);
   return LIS_E_INVALID;
 }
 

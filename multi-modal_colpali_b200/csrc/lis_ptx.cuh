@@ -79,16 +79,18 @@ __device__ __forceinline__ void lis_timeout_trap() {
 }
 // Bounded wait: a pipeline bug must surface as a launch failure, never as a hung GPU.
 // ~4e9 SM cycles is about 2 s at boost clock; every legitimate wait is microseconds.
+// The report is a separate, never-inlined function: the waits are inlined at dozens of sites of the hot kernels, and a
+// printf call sequence at each of them cost more instruction-cache space than the loops around them.
+static __device__ __noinline__ void mbar_timeout_report(uint32_t bar, uint32_t parity) {
+  printf("lis: mbarrier wait timed out (block %d thread %d bar smem 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+  lis_timeout_trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
-      printf("lis: mbarrier wait timed out (block %d thread %d bar smem 0x%x parity %u)\n", blockIdx.x,
-             threadIdx.x, smem_u32(bar), parity);
-      lis_timeout_trap();
-    }
+    if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) mbar_timeout_report(smem_u32(bar), parity);
   }
 }
 
@@ -112,11 +114,7 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait_u32(bar, parity)) {
-    if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
-      printf("lis: mbarrier wait timed out (block %d thread %d bar smem 0x%x parity %u)\n", blockIdx.x, threadIdx.x,
-             bar, parity);
-      lis_timeout_trap();
-    }
+    if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) mbar_timeout_report(bar, parity);
   }
 }
 

@@ -122,6 +122,83 @@ __device__ __forceinline__ float max32_split(const uint32_t (&v)[32], float m, i
   return fmaxf(a0, a1);
 }
 
+// One page ends inside this 32-column chunk, at column b (0 < b < 32, the same for the whole warp): columns [0, b)
+// go into the running maximum of the page that ends, [b, 32) into that of the next page.  Two fall-through switches
+// execute exactly b and 32 - b FMNMX -- a quarter of the instructions of the select-based max32_split.
+__device__ __forceinline__ void max32_cut(const uint32_t (&v)[32], int b, float& m_old, float& m_new) {
+  float a = m_old, c = m_new;
+  switch (b) {
+    case 31: a = fmaxf(a, __uint_as_float(v[30]));
+    case 30: a = fmaxf(a, __uint_as_float(v[29]));
+    case 29: a = fmaxf(a, __uint_as_float(v[28]));
+    case 28: a = fmaxf(a, __uint_as_float(v[27]));
+    case 27: a = fmaxf(a, __uint_as_float(v[26]));
+    case 26: a = fmaxf(a, __uint_as_float(v[25]));
+    case 25: a = fmaxf(a, __uint_as_float(v[24]));
+    case 24: a = fmaxf(a, __uint_as_float(v[23]));
+    case 23: a = fmaxf(a, __uint_as_float(v[22]));
+    case 22: a = fmaxf(a, __uint_as_float(v[21]));
+    case 21: a = fmaxf(a, __uint_as_float(v[20]));
+    case 20: a = fmaxf(a, __uint_as_float(v[19]));
+    case 19: a = fmaxf(a, __uint_as_float(v[18]));
+    case 18: a = fmaxf(a, __uint_as_float(v[17]));
+    case 17: a = fmaxf(a, __uint_as_float(v[16]));
+    case 16: a = fmaxf(a, __uint_as_float(v[15]));
+    case 15: a = fmaxf(a, __uint_as_float(v[14]));
+    case 14: a = fmaxf(a, __uint_as_float(v[13]));
+    case 13: a = fmaxf(a, __uint_as_float(v[12]));
+    case 12: a = fmaxf(a, __uint_as_float(v[11]));
+    case 11: a = fmaxf(a, __uint_as_float(v[10]));
+    case 10: a = fmaxf(a, __uint_as_float(v[9]));
+    case 9: a = fmaxf(a, __uint_as_float(v[8]));
+    case 8: a = fmaxf(a, __uint_as_float(v[7]));
+    case 7: a = fmaxf(a, __uint_as_float(v[6]));
+    case 6: a = fmaxf(a, __uint_as_float(v[5]));
+    case 5: a = fmaxf(a, __uint_as_float(v[4]));
+    case 4: a = fmaxf(a, __uint_as_float(v[3]));
+    case 3: a = fmaxf(a, __uint_as_float(v[2]));
+    case 2: a = fmaxf(a, __uint_as_float(v[1]));
+    case 1: a = fmaxf(a, __uint_as_float(v[0]));
+    default: break;
+  }
+  switch (b) {
+    case 1: c = fmaxf(c, __uint_as_float(v[1]));
+    case 2: c = fmaxf(c, __uint_as_float(v[2]));
+    case 3: c = fmaxf(c, __uint_as_float(v[3]));
+    case 4: c = fmaxf(c, __uint_as_float(v[4]));
+    case 5: c = fmaxf(c, __uint_as_float(v[5]));
+    case 6: c = fmaxf(c, __uint_as_float(v[6]));
+    case 7: c = fmaxf(c, __uint_as_float(v[7]));
+    case 8: c = fmaxf(c, __uint_as_float(v[8]));
+    case 9: c = fmaxf(c, __uint_as_float(v[9]));
+    case 10: c = fmaxf(c, __uint_as_float(v[10]));
+    case 11: c = fmaxf(c, __uint_as_float(v[11]));
+    case 12: c = fmaxf(c, __uint_as_float(v[12]));
+    case 13: c = fmaxf(c, __uint_as_float(v[13]));
+    case 14: c = fmaxf(c, __uint_as_float(v[14]));
+    case 15: c = fmaxf(c, __uint_as_float(v[15]));
+    case 16: c = fmaxf(c, __uint_as_float(v[16]));
+    case 17: c = fmaxf(c, __uint_as_float(v[17]));
+    case 18: c = fmaxf(c, __uint_as_float(v[18]));
+    case 19: c = fmaxf(c, __uint_as_float(v[19]));
+    case 20: c = fmaxf(c, __uint_as_float(v[20]));
+    case 21: c = fmaxf(c, __uint_as_float(v[21]));
+    case 22: c = fmaxf(c, __uint_as_float(v[22]));
+    case 23: c = fmaxf(c, __uint_as_float(v[23]));
+    case 24: c = fmaxf(c, __uint_as_float(v[24]));
+    case 25: c = fmaxf(c, __uint_as_float(v[25]));
+    case 26: c = fmaxf(c, __uint_as_float(v[26]));
+    case 27: c = fmaxf(c, __uint_as_float(v[27]));
+    case 28: c = fmaxf(c, __uint_as_float(v[28]));
+    case 29: c = fmaxf(c, __uint_as_float(v[29]));
+    case 30: c = fmaxf(c, __uint_as_float(v[30]));
+    case 31: c = fmaxf(c, __uint_as_float(v[31]));
+    default: break;
+  }
+  m_old = a;
+  m_new = c;
+}
+
 // first index i in [0, n] with off[i] >= target (off ascending, n+1 entries)
 __device__ __forceinline__ int64_t lower_bound_off(const int64_t* off, int64_t n, int64_t target) {
   int64_t lo = 0, hi = n;  // answer in [lo, hi]; off[n] >= any target we pass
@@ -141,7 +218,8 @@ __device__ __forceinline__ int64_t lower_bound_off(const int64_t* off, int64_t n
 // the tile's segment table, so every kernel form produces the same bits.
 // [rbase, rbase + rcnt): tile rows this CTA owns (the whole tile, or 64 rows of a split tile: segments of the
 // other half are skipped; a segment straddling the boundary is a planning error and traps).
-__device__ __forceinline__ void reduce_tile_segments(const float* ex, int nparts, int pstride, const uint16_t* tab16,
+template <int NPARTS>
+__device__ __forceinline__ void reduce_tile_segments(const float* ex, int pstride, const uint16_t* tab16,
                                                      const int32_t* g_lo, const int32_t* g_hi, int seg_first, int seg_cnt,
                                                      int tile_row0, int rbase, int rcnt, bool clamp, bool round_ref,
                                                      bool round_sum, int is_bf16, float* out_col, int64_t ld_out,
@@ -170,15 +248,50 @@ __device__ __forceinline__ void reduce_tile_segments(const float* ex, int nparts
       }
       if (!mine) { lo = 0; hi = 0; }
     }
-    float acc = 0.f;
-    for (int r = lo + sub; r < hi; r += G) {
-      float x = ex[r];
-      for (int c = 1; c < nparts; ++c) x = fmaxf(x, ex[c * pstride + r]);
-      if (clamp) x = fmaxf(x, 0.f);
-      if (round_ref) x = round_to_input_dtype(x, is_bf16);
-      acc += x;
+    // Canonical order, independent of how many segments share the tile (so a query scores the same bits alone or
+    // coalesced with others): eight interleaved partial sums A_v = x[lo+v] + x[lo+v+8] + ... (ascending rows),
+    // combined as ((A0+A4)+(A2+A6)) + ((A1+A5)+(A3+A7)) -- the xor-4, xor-2, xor-1 butterfly.  A lane owns the partial
+    // sums v = sub (mod G); it visits them in bit-reversed order and merges them pairwise (binary-counter stack), which
+    // is the upper part of the butterfly; shuffles do the rest.  One instance of the row loop, whatever G is.
+    const int nv = G >= 8 ? 1 : 8 / G;                       // partial sums per lane
+    const int shift = nv == 8 ? 0 : (nv == 4 ? 1 : (nv == 2 ? 2 : 3));
+    float acc = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < nv; ++k) {
+      const int v = sub + G * (int)(((0x73516240u >> (4 * k)) & 7u) >> shift);   // 3-bit reversal of k, cut to log2(nv) bits
+      float a = 0.f;
+      if (G < 8 || sub < 8) {
+        // rows lo+v, lo+v+8, ...: all loads first (independent), then the additions in ascending row order; adding
+        // the +0.0 of a row beyond the segment changes nothing, so a fixed trip count keeps the canonical value
+        auto row = [&](int r) {
+          float x = 0.f;
+          if (r < hi) {
+            x = ex[r];
+#pragma unroll
+            for (int c = 1; c < NPARTS; ++c) x = fmaxf(x, ex[c * pstride + r]);
+            if (clamp) x = fmaxf(x, 0.f);
+            if (round_ref) x = round_to_input_dtype(x, is_bf16);
+          }
+          return x;
+        };
+        const int r0 = lo + v;
+        const float x0 = row(r0), x1 = row(r0 + 8), x2 = row(r0 + 16), x3 = row(r0 + 24);
+        a = ((x0 + x1) + x2) + x3;       // == sequential accumulation from 0
+        if (hi - lo > 32) {              // segments are at most 64 rows
+          const float x4 = row(r0 + 32), x5 = row(r0 + 40), x6 = row(r0 + 48), x7 = row(r0 + 56);
+          a = (((a + x4) + x5) + x6) + x7;
+        }
+      }
+      if (k & 1) {
+        a = s0 + a;
+        if (k & 2) {
+          a = s1 + a;
+          if (k & 4) a = s2 + a; else s2 = a;
+        } else s1 = a;
+      } else s0 = a;
+      acc = a;
     }
-    for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    for (int o = (G < 8 ? G : 8) >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (mine && sub == 0) {
       if (round_sum) acc = round_to_input_dtype(acc, is_bf16);
       out_col[(int64_t)(seg_first + j) * ld_out] = acc;
@@ -418,7 +531,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         const float* ex = srm + slot * (EH * kMTile);
         const int mt = args.mt0 + g;
         const int seg_first = seginfo[2 * g], seg_cnt = seginfo[2 * g + 1];
-        reduce_tile_segments(ex, EH, kMTile, segtab + g * 16, args.seg_lo, args.seg_hi, seg_first, seg_cnt, mt * kMTile, 0,
+        reduce_tile_segments<EH>(ex, kMTile, segtab + g * 16, args.seg_lo, args.seg_hi, seg_first, seg_cnt, mt * kMTile, 0,
                              kMTile, clamp, round_ref, round_sum, is_bf16, args.out + p, args.ld_out, lane);
         __syncwarp();
         if (lane == 0) mbar_arrive(ex_empty + slot);

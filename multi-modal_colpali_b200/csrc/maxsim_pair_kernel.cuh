@@ -11,19 +11,25 @@
 //     ring of FOUR 128-column TMEM slots, each filled by one "use" of 8 k-steps x 64 cycles:
 //       - a query-tile pair (one tile per CTA) against half h of the page tile: D[256 x 128] = A[256 x 128] B_h^T
 //         (each CTA supplies 64 of B_h's 128 rows: CTA r holds tile rows h*128 + r*64 .. +64);
-//       - for an ODD tile count, the last query tile split 64/64 rows over the pair, again against half h
-//         of the page tile: D[128 x 128] in 8 x 32 cycles, which cute's "2x2" layout (tmem_frg_2sm<M_MMA=64>)
-//         puts into 64 columns: lanes 0-63 = rows x columns [0,64), lanes 64-127 = rows x [64,128).
-//     Uses alternate between the two halves of the page tile, so use parity = half = issuing warp = draining
-//     warp set, and a slot (use & 3) always meets the same set: consecutive phases of its barriers are waited
-//     for by the same warps, which is what makes parity-only mbarrier waits unambiguous.
+//       - for an ODD tile count, the last query tile split 64/64 rows over the pair against the WHOLE page tile:
+//         D[128 x 256] in 8 x 64 cycles -- the only shape of a split tile that runs at the full tensor rate (measured,
+//         profiles/micro_mma_pair_shapes_r2.txt: M128 N256 64.0 cycles per instruction = 100 %, M128 N128 57.3 = 56 %: an
+//         instruction never takes less than ~57 cycles).  cute's "2x2" layout (tmem_frg_2sm<M_MMA=64>) puts it into 128
+//         columns: lanes 0-63 = rows x instruction columns [0,128), lanes 64-127 = rows x [128,256); instruction columns
+//         [0,128) are the leader's B rows (tile rows 0-63 and 128-191), [128,256) the peer's (64-127 and 192-255).
+//     Uses are dealt round-robin: use parity = issuing warp = draining warp set, and a slot (use & 3) always meets the
+//     same set: consecutive phases of its barriers are waited for by the same warps, which is what makes parity-only
+//     mbarrier waits unambiguous.  With an odd number of uses per page tile (2 NF + 1) the sets swap page-tile halves
+//     from one tile to the next, and take turns at the split use.
 //     Four slots matter: the round trip accumulator-free -> MMA issued -> MMAs done -> epilogue awake is
 //     ~1000+ cycles on top of the MMA time, so a ring of two 256-column slots caps the tensor pipe at
 //     ~83 % (measured); four 128-column slots cover it.
 //   * the eight epilogue warps form two sets of four (one warp per TMEM lane quarter); set s drains the
-//     uses of page-tile half s, all columns of the slot per warp.  The two warps of a scheduler are therefore
-//     in different phases most of the time (one waits for tcgen05.ld while the other reduces), and both sets
-//     drain the same amount per page tile.
+//     uses of parity s, all 128 columns of the slot per warp.  The two warps of a scheduler are therefore
+//     in different phases most of the time (one waits for tcgen05.ld while the other reduces).
+//     A page tile in which no page ends (3 of 4 for ColPali's 1030-token pages) takes the FAST path: per use
+//     wait -> 4 x tcgen05.ld -> slot handed back -> 64 FMNMX3 into a statically indexed running maximum, unrolled
+//     over the query-tile groups, no page bookkeeping at all.  Tiles with a page end run the general path.
 //
 // Each CTA owns the scores of ITS query rows for all pages of the pair's range, so every output
 // element still has exactly one writer.  Segments must not straddle the 64-row midpoint of a tile
@@ -90,8 +96,8 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 constexpr int kPairWindow = 64;   // page-table window (pages)
 // exchange slots between the epilogue warps and the page reducer, and the bytes of barriers / tables / exchange
 // slots behind the operand stages: 8 and 10 resident query tiles leave exactly 3 KB next to 3 / 2 page stages
-__host__ __device__ constexpr int pair_ex_slots(int nf) { return nf >= 4 ? 2 : 4; }
-__host__ __device__ constexpr int pair_tail_bytes(int nf) { return nf >= 4 ? 3072 : 5120; }
+__host__ __device__ constexpr int pair_ex_slots(int nf) { return nf >= 4 ? 2 : 8; }
+__host__ __device__ constexpr int pair_tail_bytes(int nf) { return nf >= 4 ? 3072 : 9216; }
 
 // NF: query-tile pairs (M = 256 uses, one tile per CTA); ODD: a final tile split 64/64 over the pair (M = 128 use).
 template <int NF, bool ODD, bool DBG>
@@ -240,7 +246,7 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     if (leader && pa < pb && ntiles > 0) {
       const uint32_t fmt = args.is_bf16 ? 1u : 0u;
       const uint32_t idesc_full = make_idesc_f16(fmt, 256, 128);     // tile pair x half page tile
-      const uint32_t idesc_split = make_idesc_f16(fmt, 128, 128);    // split tile (64 rows per CTA) x half page tile
+      const uint32_t idesc_split = make_idesc_f16(fmt, 128, 256);    // split tile (64 rows per CTA) x whole page tile
       const uint32_t a_base = smem_u32(smem_a);
       const uint32_t b_base = smem_u32(smem_b);
       const uint32_t acc_full_u = smem_u32(acc_full), b_empty_u = smem_u32(b_empty);
@@ -288,10 +294,7 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           issue_use(g * kAFull, kMTile * 128, 0, idesc_full);         // page-tile half 0 (even use: issuer 0, set 0)
           issue_use(g * kAFull, kMTile * 128, kBBox, idesc_full);     // half 1
         }
-        if (ODD) {                                                    // split tile: two short uses (8 x 32 cycles)
-          issue_use(NF * kAFull, 8192, 0, idesc_split);
-          issue_use(NF * kAFull, 8192, kBBox, idesc_split);
-        }
+        if (ODD) issue_use(NF * kAFull, 8192, 0, idesc_split);       // split tile x whole page tile: one full-rate use
         // hand the page tile back to both producers once this warp's MMAs on it are done
         if (LIS_ISSUE_PRED) {
           if (issued) umma_commit_pair(b_empty_u + s * 8);
@@ -327,9 +330,12 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const int rcnt = split ? 64 : kMTile;
         const int seg_first = seginfo[2 * g], seg_cnt = seginfo[2 * g + 1];
         // partial maxima: [warp set][row] for a tile pair, [warp set][lane half][row] for the split tile
-        reduce_tile_segments(ex, split ? 4 : 2, split ? 64 : kMTile, segtab + g * 16, args.seg_lo, args.seg_hi, seg_first,
-                             seg_cnt, mt * kMTile, rbase, rcnt, clamp, round_ref, round_sum, is_bf16, args.out + p,
-                             args.ld_out, lane);
+        if (split)
+          reduce_tile_segments<4>(ex, 64, segtab + g * 16, args.seg_lo, args.seg_hi, seg_first, seg_cnt, mt * kMTile, rbase, rcnt,
+                                  clamp, round_ref, round_sum, is_bf16, args.out + p, args.ld_out, lane);
+        else
+          reduce_tile_segments<2>(ex, kMTile, segtab + g * 16, args.seg_lo, args.seg_hi, seg_first, seg_cnt, mt * kMTile, rbase,
+                                  rcnt, clamp, round_ref, round_sum, is_bf16, args.out + p, args.ld_out, lane);
         __syncwarp();
         if (lane == 0) mbar_arrive(ex_empty + slot);
       }
@@ -387,10 +393,13 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     // Publish one finished page of group g: this thread's partial row maximum goes into the next exchange
     // slot; the reducer takes over once all eight warps have arrived.  Nobody waits for anybody here
     // unless the ring of kEx slots is full.
+    long long st_wait = 0, st_hold = 0, st_hold_split = 0, st_wait_split = 0, st_n_split = 0, st_slow = 0, st_nslow = 0, st_fin = 0;
     uint32_t fin = 0;
     auto finish_page = [&](int g, int pi, float v) {
       const uint32_t slot = fin % kEx;
+      const long long fw0 = LIS_STATS_ON(args) ? clock64() : 0;
       mbar_wait_u32(ex_empty_u + slot * 8, ((fin / kEx) & 1u) ^ 1u);
+      if (LIS_STATS_ON(args)) st_fin += clock64() - fw0;
       srm[slot * (2 * kMTile) + etid] = v;
       if (etid == 0) {
         ex_meta[2 * slot] = pa + pi;
@@ -401,7 +410,6 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       ++fin;
     };
 
-    long long st_wait = 0, st_hold = 0, st_hold_split = 0, st_wait_split = 0, st_n_split = 0;
     if (pa < pb) {
       int p = 0;
       refill(0);
@@ -414,13 +422,127 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const int tcol = t * NT;
         auto rel_end = [&](int e) { const int d = e - tcol; return d > NT ? NT + 1 : d; };
         const int pe_tile = rel_end(pend);
-        int p_next = p, pend_next = pend;
 
-        // One query-tile group against this page tile.  Every warp walks the pages that end inside the
-        // tile (it must publish its partial maxima for each of them); at most one use of the group is its own.
-        auto do_group = [&](const int g, const bool split) {
-          int pp = p, ppend = pend;
-          bool live = pp < npages;
+        // Take this set's use `my_use`: all 128 columns of the slot into registers, slot handed back at once.
+        auto take_use = [&](const uint32_t my_use, const bool split, uint32_t (&v0)[32], uint32_t (&v1)[32],
+                            uint32_t (&v2)[32], uint32_t (&v3)[32]) {
+          const uint32_t slot = my_use & (NACC - 1);
+          const long long ec0 = st_on ? clock64() : 0;
+          mbar_wait_u32(acc_full_u + slot * 8, (my_use / NACC) & 1u);
+          const long long ec1 = st_on ? clock64() : 0;
+          tc_fence_after();
+          const uint32_t taddr = tlane + slot * kSlotCols;
+          tmem_ld32(taddr, v0);
+          tmem_ld32(taddr + 32, v1);
+          tmem_ld32(taddr + 64, v2);
+          tmem_ld32(taddr + 96, v3);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_u32(acc_empty_l + slot * 8);    // slot back to the MMA warps
+          if (st_on) { st_wait += ec1 - ec0; const long long hc = clock64() - ec1; st_hold += hc; if (split) { st_hold_split += hc; st_wait_split += ec1 - ec0; ++st_n_split; } }
+        };
+
+        const bool live_tile = p < npages;
+        // (votes make the path selection a warp-uniform branch: no convergence-barrier bookkeeping around the loop body)
+        if (!DBG && __all_sync(0xffffffffu, !live_tile || pe_tile > NT)) {
+          // ---------- FAST path: no page ends inside this tile.  Unrolled over the groups: rm[g] is a fixed register.
+#pragma unroll
+          for (int g = 0; g < NF; ++g) {
+            // uses 2g (tile half 0) and 2g+1 (half 1) of this tile; the one whose parity equals `set` is ours
+            const uint32_t my_use = use_base + ((use_base ^ (uint32_t)set) & 1u);
+            use_base += 2u;
+            uint32_t v0[32], v1[32], v2[32], v3[32];
+            take_use(my_use, false, v0, v1, v2, v3);
+            if (live_tile) {
+              float m = rm[g];
+              m = max32(v0, m);
+              m = max32(v1, m);
+              m = max32(v2, m);
+              m = max32(v3, m);
+              rm[g] = m;
+            }
+          }
+          if (ODD) {
+            const bool own = (use_base & 1u) == (uint32_t)set;      // the sets take turns at the split use
+            const uint32_t my_use = use_base;
+            use_base += 1u;
+            if (own) {
+              uint32_t v0[32], v1[32], v2[32], v3[32];
+              take_use(my_use, true, v0, v1, v2, v3);
+              if (live_tile) {
+                float m = rm[NF];
+                m = max32(v0, m);
+                m = max32(v1, m);
+                m = max32(v2, m);
+                m = max32(v3, m);
+                rm[NF] = m;
+              }
+            }
+          }
+          continue;
+        }
+
+        // ---------- ONE page ends inside this tile (at tile column e) and the next page reaches beyond it: the only
+        // kind of page-end tile a corpus of pages longer than 256 tokens produces (ColPali: every fourth tile).  The page
+        // structure is the same for all groups, so it is resolved once here; per group a warp folds its chunks into the
+        // ending page (columns < e) or into the next one (columns >= e), publishes the former and keeps the latter.
+        if (!DBG && __all_sync(0xffffffffu, pe_tile > 0 && p + 1 < npages && p + 1 < w0 + kPW && p >= w0 &&
+                                                pw_end[p + 1 < w0 + kPW && p + 1 >= w0 ? p + 1 - w0 : 0] - tcol > NT)) {
+          const long long sl0 = st_on ? clock64() : 0;
+          const int e = pe_tile;
+#pragma unroll 1
+          for (int g = 0; g < U; ++g) {
+            const bool split = ODD && g == NF;
+            uint32_t my_use = use_base;
+            int cb0, cb1;
+            bool have = true;
+            if (!split) {
+              const int h = (int)((use_base ^ (uint32_t)set) & 1u);
+              my_use = use_base + (uint32_t)h;
+              cb0 = h * 128; cb1 = cb0 + 64;
+            } else {
+              have = (use_base & 1u) == (uint32_t)set;
+              cb0 = lhalf * 64; cb1 = 128 + lhalf * 64;
+            }
+            use_base += split ? 1u : 2u;
+            float m_old = rm[0], m_new = -INFINITY;
+            if (have) {
+              uint32_t v0[32], v1[32], v2[32], v3[32];
+              take_use(my_use, split, v0, v1, v2, v3);
+              auto fold = [&](const uint32_t (&v)[32], const int cb) {
+                const int d = e - cb;
+                if (d >= 32) m_old = max32(v, m_old);
+                else if (d <= 0) m_new = max32(v, m_new);
+                else max32_cut(v, d, m_old, m_new);
+              };
+              fold(v0, cb0);
+              fold(v1, cb0 + 32);
+              fold(v2, cb1);
+              fold(v3, cb1 + 32);
+            }
+            finish_page(g, p, m_old);
+            rotate(m_new);
+          }
+          ++p;
+          pend = pw_end[p - w0];
+          if (st_on) { st_slow += clock64() - sl0; ++st_nslow; }
+          continue;
+        }
+
+        // ---------- general path: pages end inside this tile.  One query-tile group at a time (ONE instance of the
+        // code: a runtime loop over the groups); every warp walks the pages that end inside the tile (it must publish its
+        // partial maxima for each of them); at most one use of the group is its own.  Each group consumes rm[0] and
+        // pushes the new running maximum to the back, so after the U groups of a tile the ring is back in the order
+        // the fast path indexes.
+        const long long sl0 = st_on ? clock64() : 0;
+        int pp = p, ppend = pend;
+        if (live_tile && (p < w0 || p >= w0 + kPW)) refill(p);   // (rare) cursor rewound out of the window
+#pragma unroll 1
+        for (int g = 0; g < U; ++g) {
+          const bool split = ODD && g == NF;
+          pp = p; ppend = pend;
+          bool live = live_tile;
           int pe = pe_tile;
           float m = rm[0];
 
@@ -446,20 +568,14 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
               }
             }
             if (!live) return;
-            if (pe - cb > 32) { m = max32(v, m); return; }
-            int lo = pe - cb;
-            float m_next;
-            m = max32_split(v, m, lo, m_next);
-            finish_page(g, pp, m);
-            next_page();
-            if (!live) return;
-            if (pe - cb > 32) { m = m_next; return; }
+            if (pe - cb > 32) { m = max32(v, m); return; }   // no page ends inside this chunk
+            int lo = 0;                                      // (pe > cb here: earlier pages were closed already)
             while (true) {
-              const int rel = pe - cb;
+              const int rel = pe - cb;                       // > 32: the page continues behind this chunk
               const int hi = rel < 32 ? rel : 32;
               m = max32_masked(v, m, lo, hi);
               if (rel > 32) break;
-              finish_page(g, pp, m);
+              finish_page(g, pp, m);                         // the page ended inside (or exactly at the end of) the chunk
               next_page();
               if (!live) break;
               lo = hi;
@@ -467,59 +583,43 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             }
           };
 
-          if (live && (p < w0 || p >= w0 + kPW)) refill(p);   // (rare) cursor rewound out of the window
-          // Every group has two uses, one per half of the page tile, and set s takes half s: a tile pair fills all
-          // 128 columns of its slot (4 chunks per warp); the split tile (M = 128 over the pair, N = 128) fills 64
-          // columns, lanes 0-63 = this CTA's rows x tile columns [s*128, +64), lanes 64-127 = the same rows x the next 64.
-          const uint32_t my_use = use_base + (uint32_t)set;
-          const int nch = split ? 2 : 4;
-          const int cb0 = split ? set * 128 + lhalf * 64 : set * 128;
-          use_base += 2u;
-          {
-            const uint32_t slot = my_use & (NACC - 1);
-            const long long ec0 = st_on ? clock64() : 0;
-            mbar_wait_u32(acc_full_u + slot * 8, (my_use / NACC) & 1u);
-            const long long ec1 = st_on ? clock64() : 0;
-            tc_fence_after();
-            const uint32_t taddr = tlane + slot * kSlotCols;
+          // Which use of this group, if any, belongs to this warp's set, and which tile columns it covers: a tile pair
+          // has one use per half of the page tile (128 consecutive tile columns); the split tile has ONE use over the
+          // whole page tile, in which this warp's lanes hold tile columns [lhalf*64, +64) and [128 + lhalf*64, +64).
+          uint32_t my_use = use_base;
+          int cb0, cb1;
+          bool have = true;
+          if (!split) {
+            const int h = (int)((use_base ^ (uint32_t)set) & 1u);
+            my_use = use_base + (uint32_t)h;
+            cb0 = h * 128; cb1 = cb0 + 64;
+          } else {
+            have = (use_base & 1u) == (uint32_t)set;
+            cb0 = lhalf * 64; cb1 = 128 + lhalf * 64;
+          }
+          use_base += split ? 1u : 2u;
+          if (have) {
             uint32_t v0[32], v1[32], v2[32], v3[32];
-            tmem_ld32(taddr, v0);
-            tmem_ld32(taddr + 32, v1);
-            if (!split) { tmem_ld32(taddr + 64, v2); tmem_ld32(taddr + 96, v3); }
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster_u32(acc_empty_l + slot * 8);    // slot back to the MMA warps
-            if (st_on) { st_wait += ec1 - ec0; const long long hc = clock64() - ec1; st_hold += hc; if (split) { st_hold_split += hc; st_wait_split += ec1 - ec0; ++st_n_split; } }
+            take_use(my_use, split, v0, v1, v2, v3);
             skip_to(cb0);
-            if (!DBG && (!live || pe > cb0 + nch * 32)) {
-              if (live) {                      // fast path: no page ends inside this warp's columns
-                m = max32(v0, m);
-                m = max32(v1, m);
-                if (!split) { m = max32(v2, m); m = max32(v3, m); }
-              }
-            } else {
-              scan(v0, cb0);
-              scan(v1, cb0 + 32);
-              if (!split) { scan(v2, cb0 + 64); scan(v3, cb0 + 96); }
-            }
+            scan(v0, cb0);
+            scan(v1, cb0 + 32);
+            skip_to(cb1);
+            scan(v2, cb1);
+            scan(v3, cb1 + 32);
           }
           skip_to(NT);
           rotate(m);
-          p_next = pp;
-          pend_next = ppend;
-        };
-
-#pragma unroll 1
-        for (int g = 0; g < NF; ++g) do_group(g, false);
-        if (ODD) do_group(NF, true);
-        p = p_next; pend = pend_next;
+        }
+        p = pp; pend = ppend;
+        if (st_on) { st_slow += clock64() - sl0; ++st_nslow; }
       }
       if (LIS_STATS_ON(args) && blockIdx.x < 2 && lane == 0) {
         args.stats[rank * 64 + 4 + 2 * warp] = st_wait;     // epilogue warp: waiting for a full accumulator slot
         args.stats[rank * 64 + 5 + 2 * warp] = st_hold;     //                wake -> release
         if (warp == 0) args.stats[rank * 64 + 26] = clock64() - st_t0;
         if (warp == 0 || warp == 4) { args.stats[rank * 64 + 28 + warp] = st_hold_split; args.stats[rank * 64 + 29 + warp] = st_n_split; args.stats[rank * 64 + 30 + warp] = st_wait_split; }
+        if (warp == 0 || warp == 4) { args.stats[rank * 64 + 40 + warp] = st_slow; args.stats[rank * 64 + 41 + warp] = st_nslow; args.stats[rank * 64 + 42 + warp] = st_fin; args.stats[rank * 64 + 43 + warp] = ntiles; }
       }
       while (p < npages) {          // pages not closed by any tile: trailing empty pages (or ntiles == 0)
         if (p < w0 || p >= w0 + kPW) refill(p);

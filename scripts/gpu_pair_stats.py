@@ -42,6 +42,10 @@ for nq, qtok in [(8, 32), (12, 32), (32, 20), (24, 32)]:
                         "split_use_hold_wait_n_w0": [s[28] / max(s[29], 1), s[30] / max(s[29], 1), s[29]],
                         "split_use_hold_wait_n_w4": [s[32] / max(s[33], 1), s[34] / max(s[33], 1), s[33]],
                         "all_use_hold_w0_w4_per_own_use": [2 * s[5] / uses, 2 * s[5 + 8] / uses],
-                        "all_use_wait_w0_w4_per_own_use": [2 * s[4] / uses, 2 * s[4 + 8] / uses]})
+                        "all_use_wait_w0_w4_per_own_use": [2 * s[4] / uses, 2 * s[4 + 8] / uses],
+                        "slow_tiles_w0": {"cycles_per_slow_tile": s[40] / max(s[41], 1), "n_slow": s[41], "n_tiles": s[43],
+                                          "fin_wait_total": s[42], "share_of_loop": s[40] / max(s[26], 1)},
+                        "slow_tiles_w4": {"cycles_per_slow_tile": s[44] / max(s[45], 1), "n_slow": s[45], "n_tiles": s[47],
+                                          "fin_wait_total": s[46], "share_of_loop": s[44] / max(s[26], 1)}})
         print(json.dumps(rec), flush=True)
 lib.lis_set_tuning(0, 0, 0, 0, 0)

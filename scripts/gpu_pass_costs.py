@@ -14,7 +14,7 @@ pages = 60_000
 idx = lis.LateInteractionIndex(pages * 1030, pages, device=dev)
 idx.fill_synthetic(pages, 1030, seed=7)
 store = idx._as_store()
-cases = [("single", n, (0, n, 0, 0, 1)) for n in (1, 2, 3)] + [("pair", n, (0, n, 0, 0, 3)) for n in (2, 3, 4, 5, 6, 8, 10)]
+cases = [("single", n, (0, n, 0, 0, 1)) for n in (1, 2, 3)] + [("pair", n, (0, n, 0, 0, 3)) for n in (2, 3, 4, 5, 6, 7, 8, 9, 10)]
 for rnd in range(2):
     for name, n, tun in (cases if rnd == 0 else cases[::-1]):
         q = torch.nn.functional.normalize(torch.randn(n * 4, 32, 128, generator=torch.Generator().manual_seed(1)), dim=-1).to(torch.bfloat16).to(dev)

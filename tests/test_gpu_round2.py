@@ -357,19 +357,31 @@ def test_maxsim_client_fp32_growth_and_upsert_by_id(lis, oracle):
     assert client.count("c") == n
     cos = [unit(p) for p in raw]                                        # what Distance.COSINE stores
     q = torch.randn(19, 128, generator=g)
-    want = oracle.score_multi_vector([unit(q)], cos, batch_size=10 ** 9)[0]        # fp32 reference on the stored vectors
+
+    def qdrant_maxsim(qv, pages):
+        """Qdrant's MAX_SIM comparator on the stored (cosine-normalised) multivectors: sum over query vectors of the
+        best dot product among the page's OWN vectors -- no padding rows, unlike score_multi_vector's batches."""
+        return torch.stack([(unit(qv) @ pg.T).max(dim=1).values.sum() for pg in pages])
+
+    want = qdrant_maxsim(q, cos)
     res = client.query_points("c", q.tolist(), limit=10)
     wv, wi = oracle.topk(want[None], 10)
     assert [int(p.id[1:]) for p in res.points] == wi[0].tolist()
     assert max(abs(p.score - v) for p, v in zip(res.points, wv[0].tolist())) <= TOL_F32     # fp32 planes: no 1e-2 slack
     # replace a point: the old version must disappear, the count must not change
     best = wi[0, 0].item()
-    client.upsert("c", [lis.PointStruct(id=f"p{best}", vector=(-unit(q)).tolist(), payload={"page_no": best, "v": 2})])
+    newvec = torch.randn(33, 128, generator=g)
+    client.upsert("c", [lis.PointStruct(id=f"p{best}", vector=newvec.tolist(), payload={"page_no": best, "v": 2})])
     assert client.count("c") == n
+    cos2 = list(cos)
+    cos2[best] = unit(newvec)
+    want2 = qdrant_maxsim(q, cos2)
+    wv2, wi2 = oracle.topk(want2[None], n)
     res2 = client.query_points("c", q.tolist(), limit=n)
     ids2 = [int(p.id[1:]) for p in res2.points]
-    assert len(ids2) == n and len(set(ids2)) == n and ids2[0] == wi[0, 1].item()
-    assert res2.points[-1].id == f"p{best}" and res2.points[-1].payload["v"] == 2      # anti-aligned now: last
+    assert ids2 == wi2[0].tolist() and len(set(ids2)) == n              # one entry per point id: the old version is gone
+    assert max(abs(p.score - v) for p, v in zip(res2.points, wv2[0].tolist())) <= TOL_F32
+    assert [p.payload.get("v") for p in res2.points if p.id == f"p{best}"] == [2]
     # filters only see current versions
     res3 = client.query_points("c", q.tolist(), limit=n,
                                query_filter={"must": [{"key": "username", "match": {"value": "bob"}}]})
