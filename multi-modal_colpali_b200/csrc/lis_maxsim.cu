@@ -349,10 +349,11 @@ static void build_pass_plan(const Tuning& tn, int64_t n_mtiles, bool must_single
   } else {
     // auto: the cheapest decomposition of n_mtiles by the measured steady-state cost of one pass of each
     // form (ms per 60 000 ColPali pages on a power-capped B200, scripts/gpu_pass_costs.py -> profiles/).
-    // One CTA per SM wins up to 3 tiles (a single tile is HBM-bound); CTA pairs win from 4 tiles on,
-    // even tile counts being the efficient ones (no split tile); 8 and 10 tiles amortise the page stream a little more.
-    static const float cost_single[4] = {0.f, 2.65f, 4.00f, 5.28f};
-    static const float cost_pair[11] = {0.f, 0.f, 4.05f, 5.73f, 6.58f, 8.83f, 9.30f, 11.9f, 12.33f, 14.9f, 15.20f};
+    // One CTA per SM up to 3 tiles (a single tile is HBM-bound; at 2 and 3 tiles the two forms tie); CTA pairs from 4
+    // tiles on, every count 4..10 in ONE pass (an odd count ends with the full-rate N = 256 use of the split tile);
+    // 8 and 10 tiles amortise the page stream a little more.
+    static const float cost_single[4] = {0.f, 2.65f, 3.90f, 5.40f};
+    static const float cost_pair[11] = {0.f, 0.f, 4.05f, 5.45f, 6.35f, 8.05f, 8.95f, 10.75f, 11.90f, 14.00f, 14.90f};   // round-2 kernel
     const int gcap = tn.group ? tn.group : 10;    // group = most tiles a pass may hold
     std::vector<float> best((size_t)n_mtiles + 1, 1e30f);
     std::vector<int8_t> choice((size_t)n_mtiles + 1, 0);       // +n = single pass of n tiles, -n = pair pass

@@ -106,97 +106,23 @@ __device__ __forceinline__ float max32_masked(const uint32_t (&v)[32], float m, 
 }
 
 // one pass over a chunk in which a page ends at column b (0..32): returns max(m, v[0..b)) and puts
-// max(v[b..32)) -- the start of the next page -- into m_next
+// max(v[b..32)) -- the start of the next page -- into m_next.  Branch-free (b is the same for the whole warp, but a
+// switch on it compiles into a tree of indirect jumps that costs ~1000 cycles): per pair of columns two selects and
+// one FMNMX3 per side, four independent chains.
 __device__ __forceinline__ float max32_split(const uint32_t (&v)[32], float m, int b, float& m_next) {
   float a0 = m, a1 = -INFINITY, c0 = -INFINITY, c1 = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < 32; i += 2) {
+  for (int i = 0; i < 32; i += 4) {
     const float x0 = __uint_as_float(v[i]), x1 = __uint_as_float(v[i + 1]);
-    const bool p0 = i < b, p1 = i + 1 < b;
-    a0 = fmaxf(a0, p0 ? x0 : -INFINITY);
-    c0 = fmaxf(c0, p0 ? -INFINITY : x0);
-    a1 = fmaxf(a1, p1 ? x1 : -INFINITY);
-    c1 = fmaxf(c1, p1 ? -INFINITY : x1);
+    const float x2 = __uint_as_float(v[i + 2]), x3 = __uint_as_float(v[i + 3]);
+    const bool p0 = i < b, p1 = i + 1 < b, p2 = i + 2 < b, p3 = i + 3 < b;
+    a0 = fmax3(a0, p0 ? x0 : -INFINITY, p1 ? x1 : -INFINITY);
+    c0 = fmax3(c0, p0 ? -INFINITY : x0, p1 ? -INFINITY : x1);
+    a1 = fmax3(a1, p2 ? x2 : -INFINITY, p3 ? x3 : -INFINITY);
+    c1 = fmax3(c1, p2 ? -INFINITY : x2, p3 ? -INFINITY : x3);
   }
   m_next = fmaxf(c0, c1);
   return fmaxf(a0, a1);
-}
-
-// One page ends inside this 32-column chunk, at column b (0 < b < 32, the same for the whole warp): columns [0, b)
-// go into the running maximum of the page that ends, [b, 32) into that of the next page.  Two fall-through switches
-// execute exactly b and 32 - b FMNMX -- a quarter of the instructions of the select-based max32_split.
-__device__ __forceinline__ void max32_cut(const uint32_t (&v)[32], int b, float& m_old, float& m_new) {
-  float a = m_old, c = m_new;
-  switch (b) {
-    case 31: a = fmaxf(a, __uint_as_float(v[30]));
-    case 30: a = fmaxf(a, __uint_as_float(v[29]));
-    case 29: a = fmaxf(a, __uint_as_float(v[28]));
-    case 28: a = fmaxf(a, __uint_as_float(v[27]));
-    case 27: a = fmaxf(a, __uint_as_float(v[26]));
-    case 26: a = fmaxf(a, __uint_as_float(v[25]));
-    case 25: a = fmaxf(a, __uint_as_float(v[24]));
-    case 24: a = fmaxf(a, __uint_as_float(v[23]));
-    case 23: a = fmaxf(a, __uint_as_float(v[22]));
-    case 22: a = fmaxf(a, __uint_as_float(v[21]));
-    case 21: a = fmaxf(a, __uint_as_float(v[20]));
-    case 20: a = fmaxf(a, __uint_as_float(v[19]));
-    case 19: a = fmaxf(a, __uint_as_float(v[18]));
-    case 18: a = fmaxf(a, __uint_as_float(v[17]));
-    case 17: a = fmaxf(a, __uint_as_float(v[16]));
-    case 16: a = fmaxf(a, __uint_as_float(v[15]));
-    case 15: a = fmaxf(a, __uint_as_float(v[14]));
-    case 14: a = fmaxf(a, __uint_as_float(v[13]));
-    case 13: a = fmaxf(a, __uint_as_float(v[12]));
-    case 12: a = fmaxf(a, __uint_as_float(v[11]));
-    case 11: a = fmaxf(a, __uint_as_float(v[10]));
-    case 10: a = fmaxf(a, __uint_as_float(v[9]));
-    case 9: a = fmaxf(a, __uint_as_float(v[8]));
-    case 8: a = fmaxf(a, __uint_as_float(v[7]));
-    case 7: a = fmaxf(a, __uint_as_float(v[6]));
-    case 6: a = fmaxf(a, __uint_as_float(v[5]));
-    case 5: a = fmaxf(a, __uint_as_float(v[4]));
-    case 4: a = fmaxf(a, __uint_as_float(v[3]));
-    case 3: a = fmaxf(a, __uint_as_float(v[2]));
-    case 2: a = fmaxf(a, __uint_as_float(v[1]));
-    case 1: a = fmaxf(a, __uint_as_float(v[0]));
-    default: break;
-  }
-  switch (b) {
-    case 1: c = fmaxf(c, __uint_as_float(v[1]));
-    case 2: c = fmaxf(c, __uint_as_float(v[2]));
-    case 3: c = fmaxf(c, __uint_as_float(v[3]));
-    case 4: c = fmaxf(c, __uint_as_float(v[4]));
-    case 5: c = fmaxf(c, __uint_as_float(v[5]));
-    case 6: c = fmaxf(c, __uint_as_float(v[6]));
-    case 7: c = fmaxf(c, __uint_as_float(v[7]));
-    case 8: c = fmaxf(c, __uint_as_float(v[8]));
-    case 9: c = fmaxf(c, __uint_as_float(v[9]));
-    case 10: c = fmaxf(c, __uint_as_float(v[10]));
-    case 11: c = fmaxf(c, __uint_as_float(v[11]));
-    case 12: c = fmaxf(c, __uint_as_float(v[12]));
-    case 13: c = fmaxf(c, __uint_as_float(v[13]));
-    case 14: c = fmaxf(c, __uint_as_float(v[14]));
-    case 15: c = fmaxf(c, __uint_as_float(v[15]));
-    case 16: c = fmaxf(c, __uint_as_float(v[16]));
-    case 17: c = fmaxf(c, __uint_as_float(v[17]));
-    case 18: c = fmaxf(c, __uint_as_float(v[18]));
-    case 19: c = fmaxf(c, __uint_as_float(v[19]));
-    case 20: c = fmaxf(c, __uint_as_float(v[20]));
-    case 21: c = fmaxf(c, __uint_as_float(v[21]));
-    case 22: c = fmaxf(c, __uint_as_float(v[22]));
-    case 23: c = fmaxf(c, __uint_as_float(v[23]));
-    case 24: c = fmaxf(c, __uint_as_float(v[24]));
-    case 25: c = fmaxf(c, __uint_as_float(v[25]));
-    case 26: c = fmaxf(c, __uint_as_float(v[26]));
-    case 27: c = fmaxf(c, __uint_as_float(v[27]));
-    case 28: c = fmaxf(c, __uint_as_float(v[28]));
-    case 29: c = fmaxf(c, __uint_as_float(v[29]));
-    case 30: c = fmaxf(c, __uint_as_float(v[30]));
-    case 31: c = fmaxf(c, __uint_as_float(v[31]));
-    default: break;
-  }
-  m_old = a;
-  m_new = c;
 }
 
 // first index i in [0, n] with off[i] >= target (off ascending, n+1 entries)

@@ -393,7 +393,7 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     // Publish one finished page of group g: this thread's partial row maximum goes into the next exchange
     // slot; the reducer takes over once all eight warps have arrived.  Nobody waits for anybody here
     // unless the ring of kEx slots is full.
-    long long st_wait = 0, st_hold = 0, st_hold_split = 0, st_wait_split = 0, st_n_split = 0, st_slow = 0, st_nslow = 0, st_fin = 0;
+    long long st_wait = 0, st_hold = 0, st_hold_split = 0, st_wait_split = 0, st_n_split = 0, st_slow = 0, st_nslow = 0, st_fin = 0, st_spe_take = 0, st_spe_comp = 0, st_spe_fin = 0;
     uint32_t fin = 0;
     auto finish_page = [&](int g, int pi, float v) {
       const uint32_t slot = fin % kEx;
@@ -424,18 +424,19 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const int pe_tile = rel_end(pend);
 
         // Take this set's use `my_use`: all 128 columns of the slot into registers, slot handed back at once.
-        auto take_use = [&](const uint32_t my_use, const bool split, uint32_t (&v0)[32], uint32_t (&v1)[32],
-                            uint32_t (&v2)[32], uint32_t (&v3)[32]) {
+        // v3 receives chunk `rot` of the slot, v0..v2 the chunks rot+1, rot+2, rot+3 (mod 4); rot = 3 is the plain order.
+        auto take_use = [&](const uint32_t my_use, const bool split, const uint32_t rot, uint32_t (&v0)[32],
+                            uint32_t (&v1)[32], uint32_t (&v2)[32], uint32_t (&v3)[32]) {
           const uint32_t slot = my_use & (NACC - 1);
           const long long ec0 = st_on ? clock64() : 0;
           mbar_wait_u32(acc_full_u + slot * 8, (my_use / NACC) & 1u);
           const long long ec1 = st_on ? clock64() : 0;
           tc_fence_after();
           const uint32_t taddr = tlane + slot * kSlotCols;
-          tmem_ld32(taddr, v0);
-          tmem_ld32(taddr + 32, v1);
-          tmem_ld32(taddr + 64, v2);
-          tmem_ld32(taddr + 96, v3);
+          tmem_ld32(taddr + 32u * ((rot + 1u) & 3u), v0);
+          tmem_ld32(taddr + 32u * ((rot + 2u) & 3u), v1);
+          tmem_ld32(taddr + 32u * ((rot + 3u) & 3u), v2);
+          tmem_ld32(taddr + 32u * rot, v3);
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
@@ -446,39 +447,29 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const bool live_tile = p < npages;
         // (votes make the path selection a warp-uniform branch: no convergence-barrier bookkeeping around the loop body)
         if (!DBG && __all_sync(0xffffffffu, !live_tile || pe_tile > NT)) {
-          // ---------- FAST path: no page ends inside this tile.  Unrolled over the groups: rm[g] is a fixed register.
-#pragma unroll
-          for (int g = 0; g < NF; ++g) {
-            // uses 2g (tile half 0) and 2g+1 (half 1) of this tile; the one whose parity equals `set` is ours
-            const uint32_t my_use = use_base + ((use_base ^ (uint32_t)set) & 1u);
-            use_base += 2u;
-            uint32_t v0[32], v1[32], v2[32], v3[32];
-            take_use(my_use, false, v0, v1, v2, v3);
-            if (live_tile) {
-              float m = rm[g];
-              m = max32(v0, m);
-              m = max32(v1, m);
-              m = max32(v2, m);
-              m = max32(v3, m);
-              rm[g] = m;
-            }
-          }
-          if (ODD) {
-            const bool own = (use_base & 1u) == (uint32_t)set;      // the sets take turns at the split use
-            const uint32_t my_use = use_base;
-            use_base += 1u;
-            if (own) {
+          // ---------- FAST path: no page ends inside this tile.  A runtime loop over the groups (ONE copy of the
+          // body; the running maxima rotate through rm[]): unrolling it per group made the hot loop ~1000 instructions
+          // and the page-end paths, entered every fourth tile, then started from a cold instruction cache.
+#pragma unroll 1
+          for (int g = 0; g < U; ++g) {
+            const bool split = ODD && g == NF;
+            // a tile pair: uses 2g (tile half 0) and 2g+1 (half 1), the one whose parity equals `set` is ours;
+            // the split tile: ONE use, which the sets take in turns
+            const uint32_t my_use = split ? use_base : use_base + ((use_base ^ (uint32_t)set) & 1u);
+            const bool have = !split || (use_base & 1u) == (uint32_t)set;
+            use_base += split ? 1u : 2u;
+            float m = rm[0];
+            if (have) {
               uint32_t v0[32], v1[32], v2[32], v3[32];
-              take_use(my_use, true, v0, v1, v2, v3);
+              take_use(my_use, split, 3u, v0, v1, v2, v3);
               if (live_tile) {
-                float m = rm[NF];
                 m = max32(v0, m);
                 m = max32(v1, m);
                 m = max32(v2, m);
                 m = max32(v3, m);
-                rm[NF] = m;
               }
             }
+            rotate(m);
           }
           continue;
         }
@@ -508,21 +499,40 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             use_base += split ? 1u : 2u;
             float m_old = rm[0], m_new = -INFINITY;
             if (have) {
+              // The warp's chunks start at tile columns cb0, cb0+32, cb1, cb1+32 (ascending).  Chunk c is the first one
+              // that does not lie entirely before the page end; it is cut at column b (0: it belongs to the next page
+              // altogether, 32: all four chunks belong to the page that ends).  The chunks are loaded ROTATED so that
+              // chunk c always sits in v3: one copy of the cut code serves every position of the page end.
+              int n_old = (e >= cb0 + 32) + (e >= cb0 + 64) + (e >= cb1 + 32) + (e >= cb1 + 64);
+              int b = 32;
+              if (n_old < 4) {
+                const int start = n_old < 2 ? cb0 + 32 * n_old : cb1 + 32 * (n_old - 2);
+                b = e - start;
+                if (b < 0) b = 0;
+              } else n_old = 3;
+              const uint32_t c = (uint32_t)n_old;
               uint32_t v0[32], v1[32], v2[32], v3[32];
-              take_use(my_use, split, v0, v1, v2, v3);
-              auto fold = [&](const uint32_t (&v)[32], const int cb) {
-                const int d = e - cb;
-                if (d >= 32) m_old = max32(v, m_old);
-                else if (d <= 0) m_new = max32(v, m_new);
-                else max32_cut(v, d, m_old, m_new);
-              };
-              fold(v0, cb0);
-              fold(v1, cb0 + 32);
-              fold(v2, cb1);
-              fold(v3, cb1 + 32);
+              const long long q0 = st_on ? clock64() : 0;
+              take_use(my_use, split, c, v0, v1, v2, v3);
+              const long long q1 = st_on ? clock64() : 0;
+              // v0, v1, v2 = chunks c+1, c+2, c+3 (mod 4): behind c -> next page, before c (wrapped around) -> ending page
+              const float f0 = max32(v0, -INFINITY), f1 = max32(v1, -INFINITY), f2 = max32(v2, -INFINITY);
+              const bool n0 = c + 1u < 4u, n1 = c + 2u < 4u, n2 = c + 3u < 4u;
+              m_new = fmax3(m_new, n0 ? f0 : -INFINITY, n1 ? f1 : -INFINITY);
+              m_new = fmaxf(m_new, n2 ? f2 : -INFINITY);
+              m_old = fmax3(m_old, n0 ? -INFINITY : f0, n1 ? -INFINITY : f1);
+              m_old = fmaxf(m_old, n2 ? -INFINITY : f2);
+              {   // branch-free cut (a switch on b compiles into a tree of indirect jumps, ~1000 cycles)
+                float cut_new;
+                m_old = max32_split(v3, m_old, b, cut_new);
+                m_new = fmaxf(m_new, cut_new);
+              }
+              if (st_on) { st_spe_take += q1 - q0; st_spe_comp += clock64() - q1; }
             }
+            const long long q2 = st_on ? clock64() : 0;
             finish_page(g, p, m_old);
             rotate(m_new);
+            if (st_on) st_spe_fin += clock64() - q2;
           }
           ++p;
           pend = pw_end[p - w0];
@@ -600,7 +610,7 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           use_base += split ? 1u : 2u;
           if (have) {
             uint32_t v0[32], v1[32], v2[32], v3[32];
-            take_use(my_use, split, v0, v1, v2, v3);
+            take_use(my_use, split, 3u, v0, v1, v2, v3);
             skip_to(cb0);
             scan(v0, cb0);
             scan(v1, cb0 + 32);
@@ -620,6 +630,7 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         if (warp == 0) args.stats[rank * 64 + 26] = clock64() - st_t0;
         if (warp == 0 || warp == 4) { args.stats[rank * 64 + 28 + warp] = st_hold_split; args.stats[rank * 64 + 29 + warp] = st_n_split; args.stats[rank * 64 + 30 + warp] = st_wait_split; }
         if (warp == 0 || warp == 4) { args.stats[rank * 64 + 40 + warp] = st_slow; args.stats[rank * 64 + 41 + warp] = st_nslow; args.stats[rank * 64 + 42 + warp] = st_fin; args.stats[rank * 64 + 43 + warp] = ntiles; }
+        if (warp == 0 || warp == 4) { args.stats[rank * 64 + 48 + warp] = st_spe_take; args.stats[rank * 64 + 49 + warp] = st_spe_comp; args.stats[rank * 64 + 50 + warp] = st_spe_fin; }
       }
       while (p < npages) {          // pages not closed by any tile: trailing empty pages (or ntiles == 0)
         if (p < w0 || p >= w0 + kPW) refill(p);

@@ -46,6 +46,8 @@ for nq, qtok in [(8, 32), (12, 32), (32, 20), (24, 32)]:
                         "slow_tiles_w0": {"cycles_per_slow_tile": s[40] / max(s[41], 1), "n_slow": s[41], "n_tiles": s[43],
                                           "fin_wait_total": s[42], "share_of_loop": s[40] / max(s[26], 1)},
                         "slow_tiles_w4": {"cycles_per_slow_tile": s[44] / max(s[45], 1), "n_slow": s[45], "n_tiles": s[47],
-                                          "fin_wait_total": s[46], "share_of_loop": s[44] / max(s[26], 1)}})
+                                          "fin_wait_total": s[46], "share_of_loop": s[44] / max(s[26], 1)},
+                        "spe_per_slow_tile_w0": {"take": s[48] / max(s[41], 1), "compute": s[49] / max(s[41], 1), "finish": s[50] / max(s[41], 1)},
+                        "spe_per_slow_tile_w4": {"take": s[52] / max(s[45], 1), "compute": s[53] / max(s[45], 1), "finish": s[54] / max(s[45], 1)}})
         print(json.dumps(rec), flush=True)
 lib.lis_set_tuning(0, 0, 0, 0, 0)

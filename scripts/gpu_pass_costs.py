@@ -1,6 +1,6 @@
 """Steady-state cost of ONE pass over the page store for every K1 form / resident tile count
 (the table behind the pass planner in lis_maxsim.cu).  60 000 pages x 1030 tokens."""
-import importlib, json, sys
+import importlib, json, os, sys
 from pathlib import Path
 import torch
 ROOT = Path(__file__).resolve().parent.parent
@@ -15,7 +15,7 @@ idx = lis.LateInteractionIndex(pages * 1030, pages, device=dev)
 idx.fill_synthetic(pages, 1030, seed=7)
 store = idx._as_store()
 cases = [("single", n, (0, n, 0, 0, 1)) for n in (1, 2, 3)] + [("pair", n, (0, n, 0, 0, 3)) for n in (2, 3, 4, 5, 6, 7, 8, 9, 10)]
-for rnd in range(2):
+for rnd in range(int(os.environ.get('ROUNDS', '2'))):
     for name, n, tun in (cases if rnd == 0 else cases[::-1]):
         q = torch.nn.functional.normalize(torch.randn(n * 4, 32, 128, generator=torch.Generator().manual_seed(1)), dim=-1).to(torch.bfloat16).to(dev)
         pq = scoring.pack_queries(q, dev)
