@@ -151,6 +151,7 @@ int lis_comm_init(lis_comm** out, const void* unique_id, int rank, int world, in
 
 void lis_comm_destroy(lis_comm* c) {
   if (!c) return;
+  index_release_comm(c);   // graphs that captured this communicator's all-gather must go first
   NcclApi* n = nccl_api();
   if (c->nccl && n) n->CommDestroy(c->nccl);
   delete c;

@@ -34,6 +34,9 @@ int run_tournament(const float* s, int64_t ld_s, const int64_t* ids, int64_t ld_
 // ncclAllGather of `bytes` bytes per rank (lis_comm.cu)
 int comm_all_gather(lis_comm* c, const void* send, void* recv, size_t bytes, cudaStream_t st);
 Tuning tuning_snapshot();
+// Destroy every cached search graph that captured a collective of `c` (lis_index.cu).  NCCL keeps a communicator alive
+// while a captured graph refers to it -- ncclCommDestroy would wait for ever -- so lis_comm_destroy calls this first.
+void index_release_comm(lis_comm* c);
 
 // Encode a 2-D row-major [rows, 128] 16-bit tensor with a (64 col x box_rows) box, 128-byte swizzle.
 int encode_rows_tmap(CUtensorMap* map, const void* base, int64_t rows, int box_rows, int dtype);

@@ -56,6 +56,7 @@ struct lis_index {
   uint64_t gen = 0;                     // bumped whenever a buffer above moved or the content changed
   struct Replay { cudaGraphExec_t exec; int kernels; };
   std::map<lis::GraphKey, Replay> graphs;
+  lis_comm* graph_comm = nullptr;       // the communicator whose all-gather the cached graphs captured (if any)
   int64_t graph_replays = 0, graph_captures = 0;
 };
 
@@ -123,7 +124,24 @@ static inline uint8_t* lo_plane(const lis_index* ix) {
 static void drop_graphs(lis_index* ix) {
   for (auto& kv : ix->graphs) cudaGraphExecDestroy(kv.second.exec);
   ix->graphs.clear();
+  ix->graph_comm = nullptr;
   ++ix->gen;
+}
+
+// live indexes, so that a communicator can find the graphs that captured it
+static std::mutex g_registry_mu;
+static std::vector<lis_index*> g_registry;
+
+void index_release_comm(lis_comm* c) {
+  std::lock_guard<std::mutex> reg(g_registry_mu);
+  for (lis_index* ix : g_registry) {
+    std::lock_guard<std::mutex> lock(ix->mu);
+    if (ix->graph_comm == c) {
+      cudaSetDevice(ix->device);
+      if (ix->sstream) cudaStreamSynchronize(ix->sstream);
+      drop_graphs(ix);
+    }
+  }
 }
 
 static int ensure(lis_index* ix, void** p, int64_t* have, int64_t need) {
@@ -189,12 +207,20 @@ int lis_index_create(lis_index** out, int device, int dtype, int64_t cap_rows, i
     lis_index_destroy(ix);
     return LIS_E_NOMEM;
   }
+  {
+    std::lock_guard<std::mutex> reg(g_registry_mu);
+    g_registry.push_back(ix);
+  }
   *out = ix;
   return LIS_OK;
 }
 
 void lis_index_destroy(lis_index* ix) {
   if (!ix) return;
+  {
+    std::lock_guard<std::mutex> reg(g_registry_mu);
+    g_registry.erase(std::remove(g_registry.begin(), g_registry.end(), ix), g_registry.end());
+  }
   cudaFree(ix->tokens);
   cudaFree(ix->offsets);
   cudaFree(ix->ids);
@@ -664,6 +690,7 @@ int lis_index_search_sharded(lis_index* ix, lis_comm* comm, const void* q, int64
     return LIS_OK;
   };
 
+  if (world > 1 && ix->graph_comm != nullptr && ix->graph_comm != comm) drop_graphs(ix);   // one communicator per cache
   const Tuning tn = tuning_snapshot();
   const int tune_sig = tn.tile_n * 1000003 + tn.group * 10007 + tn.max_ctas * 101 + tn.epi_halves * 17 + tn.a_operand * 5 + tn.ablate;
   const GraphKey key(q_rows, n_seg, n_mtiles, nq, ix->n_pages, ix->n_rows, k, round_mode, world, (direct ? 1 : 0) | (q_dev ? 2 : 0),
@@ -695,6 +722,7 @@ int lis_index_search_sharded(lis_index* ix, lis_comm* comm, const void* q, int64
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return LIS_E_CUDA; }
     ix->graphs[key2] = lis_index::Replay{exec, kernels};
+    if (world > 1) ix->graph_comm = comm;
     ++ix->graph_captures;
     memcpy(out_scores, ix->h_out, (size_t)nq * k * 4);
     memcpy(out_ids, ix->h_out + s_bytes, (size_t)nq * k * 8);
