@@ -116,3 +116,26 @@ if "k3" in which:
                "gbs": byts / (min(ts) * 1e-3) / 1e9, "tflops": 2.0 * n_tok * hidden * 128 / (min(ts) * 1e-3) / 1e12}
         print(json.dumps(rec), flush=True)
         out.write(json.dumps(rec) + "\n"); out.flush()
+
+if "f32" in which:
+    # fp32 embeddings (ColFlor's default dtype, 05_experiment02.py:343-347): two bf16 planes per operand, three MMAs per tile,
+    # one query tile per pass.  Algorithmic bytes: 512 B per page-token row per pass; FLOP: 3 x the bf16 path's.
+    for name, nq, qtok, pages in [("f32_c0_1q16_vs_1000x1030", 1, 16, 1000), ("f32_1q16_vs_50kx1030", 1, 16, 50_000),
+                                   ("f32_c1_32q20_vs_20kx1030", 32, 20, 20_000)]:
+        g = torch.Generator().manual_seed(1)
+        q = unit(torch.randn(nq, qtok, 128, generator=g)).to(dev)
+        pq = scoring.pack_queries(q, dev)
+        idx = lis.LateInteractionIndex(pages * 1030, pages, dtype=torch.float32, device=dev)
+        idx.fill_synthetic(pages, 1030, seed=7)
+        store = idx._as_store()
+        best, mean = time_k1(pq, store, iters=8, warm=3)
+        n_pass = pq.plan.n_mtiles
+        rows = pages * 1030
+        rec = {"case": name, "dtype": "float32 (2 bf16 planes)", "nq": nq, "qtok": qtok, "pages": pages, "passes": n_pass,
+               "ms_best": best, "ms_mean": mean, "gbs": rows * 512.0 * n_pass / (best * 1e-3) / 1e9,
+               "tflops_useful": 2.0 * nq * qtok * 128 * rows / (best * 1e-3) / 1e12,
+               "tflops_issued": 3 * 2.0 * n_pass * 128 * 128 * rows / (best * 1e-3) / 1e12,
+               "pairs_per_s": nq * pages / (best * 1e-3)}
+        print(json.dumps(rec), flush=True)
+        out.write(json.dumps(rec) + "\n"); out.flush()
+        idx.close()
