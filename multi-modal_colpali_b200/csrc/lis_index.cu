@@ -290,12 +290,15 @@ int lis_index_add(lis_index* ix, const void* tokens, const int32_t* lens, const 
     LIS_REQUIRE(tokens, "lis_index_add: null tokens");
     uint8_t* hi = static_cast<uint8_t*>(ix->tokens) + ix->n_rows * 256;
     if (ix->dtype == LIS_F32X2) {
-      float* stage = nullptr;  // fp32 rows land in a staging buffer, then get split into the planes
-      LIS_CUDA_CHECK(cudaMalloc((void**)&stage, (size_t)new_rows * 512));
+      // fp32 rows land in the index's own scratch (the search workspace, grown on demand like for a search: no
+      // allocation per call), then get split into the planes
+      std::lock_guard<std::mutex> lock(ix->mu);
+      int rc1 = ensure(ix, &ix->topk_ws, &ix->topk_ws_bytes, new_rows * 512);
+      if (rc1) return rc1;
+      float* stage = static_cast<float*>(ix->topk_ws);
       cudaError_t e = cudaMemcpyAsync(stage, tokens, (size_t)new_rows * 512, cudaMemcpyDefault, st);
       int rc2 = e == cudaSuccess ? lis_split_f32(stage, new_rows, hi, lo_plane(ix) + ix->n_rows * 256, stream) : LIS_E_CUDA;
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-      cudaFree(stage);
       if (e != cudaSuccess) { set_error("index add (fp32) failed: %s", cudaGetErrorString(e)); return LIS_E_CUDA; }
       if (rc2) return rc2;
     } else {
@@ -744,7 +747,7 @@ static int file_rows_io(lis_index* ix, bool load, int plane, int64_t row0, int64
   LIS_REQUIRE(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= (load ? ix->cap_rows : ix->n_rows), "row range out of bounds");
   LIS_REQUIRE(file_offset >= 0, "negative file offset");
   if (n_rows == 0) return LIS_OK;
-  if (io_threads <= 0) io_threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+  if (io_threads <= 0) io_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
   LIS_CUDA_CHECK(cudaSetDevice(ix->device));
   const int fd = load ? open(path, O_RDONLY) : open(path, O_WRONLY | O_CREAT, 0644);
   if (fd < 0) {

@@ -6,6 +6,7 @@
 // [128 tokens x 128 dims] tile in TMEM, and the epilogue (thread = token) adds the bias, takes the
 // row norm, scales, masks and writes the 16-bit row that goes straight into the page store.
 #include <algorithm>
+#include <cstdlib>
 
 #include "lis_common.h"
 #include "lis_ptx.cuh"
@@ -46,7 +47,7 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int is_bf16) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(kPThreads, 1)
+__global__ void __launch_bounds__(kPThreads, 2)
 project_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_w,
                const ProjectArgs args, const int NS) {
   extern __shared__ uint8_t smem_raw[];
@@ -242,11 +243,18 @@ extern "C" int lis_project_normalize(const void* hidden, int64_t n_tok, int64_t 
   LIS_CUDA_CHECK(cudaGetDevice(&dev));
   const int sms = sm_count(dev);
   LIS_REQUIRE(sms > 0, "no CUDA device");
-  const int ns = 6;
+  // Two CTAs per SM with a 3-stage ring each (from two tiles per SM on: twice the TMA issuers and two epilogues in flight per
+  // SM; measured +19..27 % at 66 k - 264 k tokens, profiles/k3_occupancy_r2.txt), or one CTA with 6 stages (small batches).
+  // LIS_K3_OCC overrides (1 | 2).
+  const int64_t ntiles_all = (n_tok + kPTile - 1) / kPTile;
+  static const int occ_env = [] { const char* e = getenv("LIS_K3_OCC"); return e ? atoi(e) : 0; }();
+  const int occ = occ_env == 1 || occ_env == 2 ? occ_env : (ntiles_all >= 2 * (int64_t)sms ? 2 : 1);
+  const int ns = occ == 2 ? 3 : 6;
+  const int smem_max = 1024 + 6 * kPStageBytes + 1024;
   const int smem = 1024 + ns * kPStageBytes + 1024;
   static std::atomic<bool> configured[64];
   if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-    LIS_CUDA_CHECK(cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LIS_CUDA_CHECK(cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
   }
   ProjectArgs a;
@@ -256,7 +264,7 @@ extern "C" int lis_project_normalize(const void* hidden, int64_t n_tok, int64_t 
   a.round_ref = round_mode == LIS_ROUND_REFERENCE;
   a.dst_row = dst_row;
   const int64_t ntiles = (n_tok + kPTile - 1) / kPTile;
-  const int grid = (int)std::min<int64_t>(sms, ntiles);
+  const int grid = (int)std::min<int64_t>((int64_t)sms * occ, ntiles);
   project_kernel<<<grid, kPThreads, smem, (cudaStream_t)stream>>>(th, tw, a, ns);
   count_launch();
   LIS_CUDA_CHECK(cudaGetLastError());
