@@ -342,6 +342,11 @@ int lis_stream_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, cons
                       const uint8_t* p_clamp_host, int64_t np, int dtype, int round_mode, float* out,
                       int64_t ld_out, int64_t chunk_rows, int host_threads, void* stream);
 void lis_stream_release(void);
+/* Pitched copy between host and device in either direction (cudaMemcpy2DAsync, cudaMemcpyDefault): `height` rows of
+ * `width_bytes` bytes.  Used to send column blocks of the [nq, np] score matrix to the caller's (pinned) result while K1 is
+ * still scoring the next block of pages -- the D2H that colpali-engine does per block with .cpu(). */
+int lis_memcpy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width_bytes,
+                       int64_t height, void* stream);
 
 #ifdef __cplusplus
 }

@@ -91,6 +91,7 @@ SIGNATURES = {
     "lis_stream_scores": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp,
                                  _i64, _i64, _i32, _vp]),
     "lis_stream_release": (None, []),
+    "lis_memcpy2d_async": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
 }
 
 _lib = None

@@ -209,6 +209,16 @@ int lis_stream_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, cons
   return LIS_OK;
 }
 
+int lis_memcpy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width_bytes, int64_t height,
+                       void* stream) {
+  LIS_REQUIRE(dst && src, "lis_memcpy2d_async: null pointer");
+  LIS_REQUIRE(width_bytes >= 0 && height >= 0 && dst_pitch >= width_bytes && src_pitch >= width_bytes, "lis_memcpy2d_async: bad shape");
+  if (width_bytes == 0 || height == 0) return LIS_OK;
+  LIS_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)width_bytes, (size_t)height,
+                                   cudaMemcpyDefault, (cudaStream_t)stream));
+  return LIS_OK;
+}
+
 void lis_stream_release(void) {
   int cur = 0;
   cudaGetDevice(&cur);

@@ -351,6 +351,39 @@ def stream_scores_host_corpus(pq: PackedQueries, ps: TensorOrList, batch_size: i
     return out
 
 
+_COPY_STREAMS: dict = {}
+
+
+def scores_to_host_overlapped(pq: PackedQueries, store: PageStore, round_mode: str, out: torch.Tensor,
+                              n_blocks: int = 4) -> torch.Tensor:
+    """K1 over `n_blocks` ranges of pages; the score columns of a finished range travel to the host result (`out`, CPU
+    float32 ``[nq, np]``, ideally pinned) on a copy stream while the next range is being scored -- the device-to-host
+    leg that colpali-engine pays per 128-page block with ``.cpu()`` (HF processing_colpali.py:362) hides behind the kernel."""
+    lib = N.load()
+    device = pq.rows.device
+    npg = store.n_pages
+    scores = torch.empty((pq.plan.nq, npg), dtype=torch.float32, device=device)
+    copy = _COPY_STREAMS.get(device.index)
+    if copy is None:
+        copy = _COPY_STREAMS[device.index] = torch.cuda.Stream(device)
+    main = torch.cuda.current_stream(device)
+    bounds = [npg * i // n_blocks for i in range(n_blocks + 1)]
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        if b <= a:
+            continue
+        sub = PageStore(store.tokens, store.offsets[a:b + 1], None if store.clamp is None else store.clamp[a:b], b - a,
+                        store.tokens_lo, store.dtype)
+        maxsim_scores_device(pq, sub, round_mode, out=scores[:, a:b])
+        ev = torch.cuda.Event()
+        ev.record(main)
+        copy.wait_event(ev)
+        N.check(lib.lis_memcpy2d_async(out.data_ptr() + 4 * a, out.stride(0) * 4, scores.data_ptr() + 4 * a, scores.stride(0) * 4,
+                                       4 * (b - a), pq.plan.nq, copy.cuda_stream))
+    copy.synchronize()
+    scores.record_stream(copy)
+    return out
+
+
 def score_multi_vector(qs: TensorOrList, ps: TensorOrList, batch_size: int = 128,
                        device: Union[str, torch.device, None] = None, *, round_mode: str = "reference",
                        return_device: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -389,6 +422,14 @@ def score_multi_vector(qs: TensorOrList, ps: TensorOrList, batch_size: int = 128
             store = build_page_store(ps, dev, pq.dtype, batch_size)
             if store.n_rows == 0:
                 raise ValueError("No passages provided")
+            if not return_device and store.n_pages >= 8192:
+                # large result: send finished column blocks to the host while the next pages are being scored
+                if out is None:
+                    out = torch.empty((pq.plan.nq, store.n_pages), dtype=torch.float32)
+                elif out.device.type != "cpu" or out.dtype != torch.float32 or tuple(out.shape) != (pq.plan.nq, store.n_pages) \
+                        or out.stride(1) != 1:
+                    raise ValueError(f"out must be a CPU float32 tensor of shape {(pq.plan.nq, store.n_pages)}")
+                return scores_to_host_overlapped(pq, store, round_mode, out)
             scores = maxsim_scores_device(pq, store, round_mode)
         if return_device:
             return scores

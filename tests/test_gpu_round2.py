@@ -467,3 +467,24 @@ def test_sharded_directory_roundtrip(lis, oracle, tmp_path, dtype):
         assert conv.payloads[4] == {"doc_id": 1, "page_id": 1, "file_name": "d1.pdf"}
         conv.close()
         lis.invalidate_dataset_index()
+
+
+# ---------------------------------------------------------------------------------------------
+# 10. large results leave the device in column blocks behind the kernel (the D2H leg of surface 1)
+# ---------------------------------------------------------------------------------------------
+def test_large_result_is_copied_out_in_blocks_behind_the_kernel(lis, oracle):
+    g = torch.Generator().manual_seed(101)
+    n_pages = 9001                                                      # >= 8192: the overlapped route
+    pages = rand_unit(g, n_pages, 9, 128).cuda()
+    qs = [rand_unit(g, n, 128) for n in (16, 70, 3)]                    # one query is cut at a 64-row boundary
+    want = oracle.score_multi_vector_widened(qs, pages.cpu())
+    got = lis.score_multi_vector(qs, pages, round_mode="f32")
+    assert got.shape == (3, n_pages) and got.device.type == "cpu" and (got - want).abs().max().item() <= TOL_F32
+    dev = lis.score_multi_vector(qs, pages, round_mode="f32", return_device=True)       # the plain route
+    assert torch.equal(dev.cpu(), got)
+    pinned = torch.empty((3, n_pages), dtype=torch.float32).pin_memory()
+    assert lis.score_multi_vector(qs, pages, round_mode="f32", out=pinned) is pinned and torch.equal(pinned, got)
+    ref16 = lis.score_multi_vector(qs, pages)                           # reference rounding through the same route
+    assert torch.equal(ref16, lis.score_multi_vector(qs, pages, return_device=True).cpu())
+    with pytest.raises(ValueError, match="out must be"):
+        lis.score_multi_vector(qs, pages, out=torch.empty(3, 5))
