@@ -543,6 +543,16 @@ page_rebase_kernel(int32_t* __restrict__ dst_row, const int64_t* __restrict__ ba
 
 static inline int64_t al256(int64_t x) { return (x + 255) & ~int64_t(255); }
 
+// Select the index's device for the duration of a call and give the caller's device back afterwards.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 static int ensure_host(uint8_t** p, int64_t* have, int64_t need) {
   if (*have >= need) return LIS_OK;
   if (*p) cudaFreeHost(*p);
@@ -593,7 +603,7 @@ int lis_index_search_sharded(lis_index* ix, lis_comm* comm, const void* q, int64
   const bool direct = seg_first == nullptr;
   const bool f32 = ix->dtype == LIS_F32X2;
   std::lock_guard<std::mutex> lock(ix->mu);
-  LIS_CUDA_CHECK(cudaSetDevice(ix->device));
+  DeviceGuard device_guard(ix->device);
   if (!ix->sstream) {
     LIS_CUDA_CHECK(cudaStreamCreateWithFlags(&ix->sstream, cudaStreamNonBlocking));
     LIS_CUDA_CHECK(cudaEventCreateWithFlags(&ix->sevent, cudaEventDisableTiming));

@@ -417,12 +417,12 @@ class LateInteractionIndex:
             raise ValueError("No queries provided")
         out_s = torch.empty((plan.nq, k), dtype=torch.float32)
         out_i = torch.empty((plan.nq, k), dtype=torch.int64)
-        with torch.cuda.device(self.device):
-            N.check(self._lib.lis_index_search_sharded(
-                self._h, comm, rows.data_ptr(), rows.shape[0], plan.seg_lo.ctypes.data, plan.seg_hi.ctypes.data,
-                plan.mt_seg.ctypes.data, plan.n_seg, plan.n_mtiles, None if plan.direct else plan.seg_first.ctypes.data,
-                plan.nq, _ROUND[round_mode], k, out_s.data_ptr(), out_i.data_ptr(),
-                _stream(self.device) if rows.is_cuda else None))
+        # (the C call selects the index's device itself; no torch device guard on this latency path)
+        N.check(self._lib.lis_index_search_sharded(
+            self._h, comm, rows.data_ptr(), rows.shape[0], plan.seg_lo.ctypes.data, plan.seg_hi.ctypes.data,
+            plan.mt_seg.ctypes.data, plan.n_seg, plan.n_mtiles, None if plan.direct else plan.seg_first.ctypes.data,
+            plan.nq, _ROUND[round_mode], k, out_s.data_ptr(), out_i.data_ptr(),
+            torch.cuda.current_stream(rows.device).cuda_stream if rows.is_cuda else None))
         return out_s, out_i
 
     def graph_stats(self) -> Tuple[int, int, int]:
