@@ -16,8 +16,10 @@ namespace lis {
 constexpr int kPTile = 128;                     // tokens per tile (UMMA M)
 constexpr int kPOut = 128;                      // output dims (UMMA N)
 constexpr int kPBlockBytes = kPTile * 128;      // one 64-feature block of A or W: 16 KB
-constexpr int kPStageBytes = 2 * kPBlockBytes;  // A block + W block
 constexpr int kPThreads = 192;
+// SUB = token sub-tiles (of 128) that share one load of every weight block: 1 -> a stage is 16 KB of h + 16 KB of W,
+// 2 -> 32 KB of h + 16 KB of W (the weight stream, which comes from L2 once per tile, is halved per token).
+__host__ __device__ constexpr int p_stage_bytes(int sub) { return (sub + 1) * kPBlockBytes; }
 
 struct ProjectArgs {
   const void* bias;     // [128] 16-bit or null
@@ -47,9 +49,13 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int is_bf16) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(kPThreads, 2)
+template <int SUB>
+__global__ void __launch_bounds__(kPThreads, SUB == 1 ? 2 : 1)
 project_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_w,
                const ProjectArgs args, const int NS) {
+  constexpr int kPStageBytes = p_stage_bytes(SUB);
+  constexpr int kRows = SUB * kPTile;            // tokens per tile
+  constexpr int kAccCols = SUB * kPOut;          // TMEM columns of one accumulator buffer
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tail = smem + (size_t)NS * kPStageBytes;
@@ -61,7 +67,7 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
   float* sbias = reinterpret_cast<float*>(tmem_slot + 2);  // [128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t ntiles = (args.n_tok + kPTile - 1) / kPTile;
+  const int64_t ntiles = (args.n_tok + kRows - 1) / kRows;
   const int kb = args.kblocks;
 
   if (threadIdx.x == 0) {
@@ -73,7 +79,7 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
   }
   if (threadIdx.x < kPOut) sbias[threadIdx.x] = args.bias ? load16(args.bias, threadIdx.x, args.is_bf16) : 0.f;
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 2 * kAccCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -90,8 +96,8 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
           mbar_wait(empty + s, ((it / NS) & 1u) ^ 1u);
           mbar_arrive_expect_tx(full + s, kPStageBytes);
           uint8_t* dst = smem + (size_t)s * kPStageBytes;
-          tma_load_2d(dst, &tmap_h, full + s, b * 64, (int32_t)(tile * kPTile), kPolicyEvictFirst);
-          tma_load_2d(dst + kPBlockBytes, &tmap_w, full + s, b * 64, 0, kPolicyEvictLast);
+          tma_load_2d(dst, &tmap_h, full + s, b * 64, (int32_t)(tile * kRows), kPolicyEvictFirst);      // SUB x 128 rows
+          tma_load_2d(dst + SUB * kPBlockBytes, &tmap_w, full + s, b * 64, 0, kPolicyEvictLast);
         }
       }
     }
@@ -110,8 +116,10 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
           const uint32_t sa = smem_u32(smem + (size_t)s * kPStageBytes);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_f16(tmem_base + a * kPOut, make_kmajor_sw128_desc(sa + k * 32),
-                     make_kmajor_sw128_desc(sa + kPBlockBytes + k * 32), idesc, (b | k) ? 1u : 0u);
+#pragma unroll
+            for (int h = 0; h < SUB; ++h)        // the sub-tiles share the weight block
+              umma_f16(tmem_base + a * kAccCols + h * kPOut, make_kmajor_sw128_desc(sa + h * kPBlockBytes + k * 32),
+                       make_kmajor_sw128_desc(sa + SUB * kPBlockBytes + k * 32), idesc, (b | k) ? 1u : 0u);
           umma_commit(empty + s);
         }
         umma_commit(acc_full + a);
@@ -125,8 +133,10 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
       const uint32_t a = use & 1u;
       mbar_wait(acc_full + a, (use >> 1) & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * kPOut;
-      const int64_t tok = tile * kPTile + row;
+#pragma unroll 1
+      for (int h = 0; h < SUB; ++h) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * kAccCols + h * kPOut;
+      const int64_t tok = tile * kRows + h * kPTile + row;
       const int rr = args.round_ref, bf = args.is_bf16;
       float ss = 0.f;
 #pragma unroll 1
@@ -175,6 +185,7 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
           }
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + a);
@@ -185,7 +196,7 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 2 * kAccCols);
   }
 }
 
@@ -234,27 +245,35 @@ extern "C" int lis_project_normalize(const void* hidden, int64_t n_tok, int64_t 
   LIS_REQUIRE(hidden_dim >= 64 && hidden_dim % 64 == 0 && hidden_dim <= 16384,
               "hidden_dim=%lld must be a multiple of 64 in [64, 16384]", (long long)hidden_dim);
   LIS_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "out is not 16-byte aligned");
-  CUtensorMap th, tw;
-  int rc = encode_2d(&th, hidden, n_tok, hidden_dim, kPTile, dtype);
-  if (rc) return rc;
-  rc = encode_2d(&tw, weight, kPOut, hidden_dim, kPOut, dtype);
-  if (rc) return rc;
   int dev = 0;
   LIS_CUDA_CHECK(cudaGetDevice(&dev));
   const int sms = sm_count(dev);
   LIS_REQUIRE(sms > 0, "no CUDA device");
-  // Two CTAs per SM with a 3-stage ring each (from two tiles per SM on: twice the TMA issuers and two epilogues in flight per
-  // SM; measured +19..27 % at 66 k - 264 k tokens, profiles/k3_occupancy_r2.txt), or one CTA with 6 stages (small batches).
-  // LIS_K3_OCC overrides (1 | 2).
-  const int64_t ntiles_all = (n_tok + kPTile - 1) / kPTile;
+  // Three launch shapes (LIS_K3_OCC overrides: 1, 2 or 3), measured in profiles/k3_occupancy_r2.txt:
+  //   small batches   one CTA per SM, 128-token tiles, 6-stage ring (latency: the ring depth matters most)
+  //   from 2 tiles/SM two CTAs per SM, 128-token tiles, 3 stages each (twice the TMA issuers, two epilogues in flight)
+  //   (override 3)    one CTA per SM, 256-token tiles that share every weight block (half the L2 -> SM weight stream):
+  //                   measured SLOWER than two CTAs per SM at every size (0.216 vs 0.179 ms at 264 k tokens) -- the weight
+  //                   stream is not what limits the kernel -- and kept only as an experiment
+  const int64_t ntiles128 = (n_tok + kPTile - 1) / kPTile;
   static const int occ_env = [] { const char* e = getenv("LIS_K3_OCC"); return e ? atoi(e) : 0; }();
-  const int occ = occ_env == 1 || occ_env == 2 ? occ_env : (ntiles_all >= 2 * (int64_t)sms ? 2 : 1);
-  const int ns = occ == 2 ? 3 : 6;
-  const int smem_max = 1024 + 6 * kPStageBytes + 1024;
-  const int smem = 1024 + ns * kPStageBytes + 1024;
+  const int shape = occ_env >= 1 && occ_env <= 3 ? occ_env
+                    : (ntiles128 >= 2 * (int64_t)sms ? 2 : 1);
+  const int sub = shape == 3 ? 2 : 1;
+  const int occ = shape == 2 ? 2 : 1;
+  const int ns = shape == 1 ? 6 : (shape == 2 ? 3 : 4);
+  const int smem = 1024 + ns * p_stage_bytes(sub) + 1024;
+  CUtensorMap th, tw;
+  int rc = encode_2d(&th, hidden, n_tok, hidden_dim, sub * kPTile, dtype);
+  if (rc) return rc;
+  rc = encode_2d(&tw, weight, kPOut, hidden_dim, kPOut, dtype);
+  if (rc) return rc;
   static std::atomic<bool> configured[64];
   if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-    LIS_CUDA_CHECK(cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    LIS_CUDA_CHECK(cudaFuncSetAttribute(project_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        1024 + 6 * p_stage_bytes(1) + 1024));
+    LIS_CUDA_CHECK(cudaFuncSetAttribute(project_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        1024 + 4 * p_stage_bytes(2) + 1024));
     if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
   }
   ProjectArgs a;
@@ -263,9 +282,10 @@ extern "C" int lis_project_normalize(const void* hidden, int64_t n_tok, int64_t 
   a.is_bf16 = dtype == LIS_BF16;
   a.round_ref = round_mode == LIS_ROUND_REFERENCE;
   a.dst_row = dst_row;
-  const int64_t ntiles = (n_tok + kPTile - 1) / kPTile;
+  const int64_t ntiles = (n_tok + sub * kPTile - 1) / (sub * kPTile);
   const int grid = (int)std::min<int64_t>((int64_t)sms * occ, ntiles);
-  project_kernel<<<grid, kPThreads, smem, (cudaStream_t)stream>>>(th, tw, a, ns);
+  if (sub == 2) project_kernel<2><<<grid, kPThreads, smem, (cudaStream_t)stream>>>(th, tw, a, ns);
+  else project_kernel<1><<<grid, kPThreads, smem, (cudaStream_t)stream>>>(th, tw, a, ns);
   count_launch();
   LIS_CUDA_CHECK(cudaGetLastError());
   return LIS_OK;
