@@ -141,6 +141,12 @@ int lis_reduce_segments(const float* seg_scores, int64_t ld_seg, const int32_t* 
  *                                  tile is loaded once per pair and shared by up to 10 query tiles).  Auto: the cheapest
  *                                  mix of passes by measured cost (one CTA per SM up to 3 tiles, pairs from 4). */
 int lis_set_tuning(int tile_n, int group, int max_ctas, int epi_halves, int a_operand);
+/* The pass planner picks, for a batch of n query tiles, the cheapest mix of passes by the cost of one pass of every form
+ * (single[1..3]: one CTA per SM with 1..3 resident tiles; pair[2..10]: CTA pairs with 2..10), in any common unit.  The
+ * built-in table was measured on a power-capped B200 (profiles/pass_costs_r2.jsonl); a deployment can measure its own
+ * (scoring.calibrate_pass_costs does) and install it here.  single has 4 entries, pair 11 (index = tile count; unused
+ * leading entries are ignored); NULL restores the defaults for that form.  Process-wide. */
+int lis_set_pass_costs(const float* single, const float* pair);
 /* Timing experiments only (scores become invalid): 1 = K1's epilogue skips the TMEM read-out, 2 = it skips
  * the max arithmetic, 3 = the producer issues no TMA loads after the first ring fill (stale tiles are reused),
  * 4 = 3 and 1 together; 0 restores normal operation.  Used by scripts/gpu_ablate.py to attribute time. */

@@ -5,7 +5,7 @@ The directory name contains a hyphen, so import it with
 ``importlib.import_module("multi-modal_colpali_b200")`` (or ``import mmcolpali_b200`` from the repo root).
 """
 from .scoring import (score_multi_vector, plan_queries, clamp_flags, maxsim_scores_device, pack_queries, build_page_store,
-                      stream_scores_host_corpus)
+                      stream_scores_host_corpus, calibrate_pass_costs)
 from .index import LateInteractionIndex, topk_device, merge_topk_device
 from .head import project_normalize
 from .reference_api import (MaxSimClient, PointStruct, QueryResponse, ScoredPoint, ensure_colpali_collection,
@@ -17,7 +17,7 @@ from .batching import QueryBatcher
 
 __all__ = [
     "score_multi_vector", "plan_queries", "clamp_flags", "maxsim_scores_device", "pack_queries", "build_page_store",
-    "stream_scores_host_corpus", "convert_embedding_cache", "invalidate_dataset_index", "Communicator", "assign_shards",
+    "stream_scores_host_corpus", "calibrate_pass_costs", "convert_embedding_cache", "invalidate_dataset_index", "Communicator", "assign_shards",
     "LateInteractionIndex", "topk_device", "merge_topk_device", "project_normalize",
     "MaxSimClient", "PointStruct", "QueryResponse", "ScoredPoint", "ensure_colpali_collection",
     "retrieve_colpali", "score_results", "index_for_dataset", "load_embedding_cache",

@@ -50,6 +50,7 @@ SIGNATURES = {
     "lis_set_tuning": (_i32, [_i32, _i32, _i32, _i32, _i32]),
     "lis_launch_count": (_i64, []),
     "lis_set_ablation": (_i32, [_i32]),
+    "lis_set_pass_costs": (_i32, [_vp, _vp]),
     "lis_k1_stats": (_i32, [_vp]),
     "lis_debug_sim_tile": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "lis_debug_sim_pair": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp]),

@@ -170,6 +170,25 @@ int lis_k1_stats(long long* device_buf) {
   g_stats = device_buf;  // 8 x int64 on the device, zeroed by the caller; null switches the counters off
   return LIS_OK;
 }
+int lis_set_pass_costs(const float* single, const float* pair) {
+  // single[1..3], pair[2..10]: cost of one pass with that many resident query tiles (same unit for both); NULL = defaults
+  std::lock_guard<std::mutex> lock(g_tuning_mu);
+  const Tuning def;
+  for (int i = 0; i < 4; ++i) g_tuning.cost_single[i] = def.cost_single[i];
+  for (int i = 0; i < 11; ++i) g_tuning.cost_pair[i] = def.cost_pair[i];
+  if (single)
+    for (int i = 1; i < 4; ++i) {
+      LIS_REQUIRE(single[i] > 0.f, "lis_set_pass_costs: single[%d] must be positive", i);
+      g_tuning.cost_single[i] = single[i];
+    }
+  if (pair)
+    for (int i = 2; i < 11; ++i) {
+      LIS_REQUIRE(pair[i] > 0.f, "lis_set_pass_costs: pair[%d] must be positive", i);
+      g_tuning.cost_pair[i] = pair[i];
+    }
+  return LIS_OK;
+}
+
 int lis_set_ablation(int mode) {
   LIS_REQUIRE(mode >= 0 && mode <= 4, "ablation mode must be in 0..4");
   std::lock_guard<std::mutex> lock(g_tuning_mu);
@@ -352,8 +371,8 @@ static void build_pass_plan(const Tuning& tn, int64_t n_mtiles, bool must_single
     // One CTA per SM up to 3 tiles (a single tile is HBM-bound; at 2 and 3 tiles the two forms tie); CTA pairs from 4
     // tiles on, every count 4..10 in ONE pass (an odd count ends with the full-rate N = 256 use of the split tile);
     // 8 and 10 tiles amortise the page stream a little more.
-    static const float cost_single[4] = {0.f, 2.65f, 3.90f, 5.40f};
-    static const float cost_pair[11] = {0.f, 0.f, 4.05f, 5.45f, 6.35f, 8.05f, 8.95f, 10.75f, 11.90f, 14.00f, 14.90f};   // round-2 kernel
+    const float* cost_single = tn.cost_single;
+    const float* cost_pair = tn.cost_pair;     // 0 = shape not available
     const int gcap = tn.group ? tn.group : 10;    // group = most tiles a pass may hold
     std::vector<float> best((size_t)n_mtiles + 1, 1e30f);
     std::vector<int8_t> choice((size_t)n_mtiles + 1, 0);       // +n = single pass of n tiles, -n = pair pass

@@ -351,6 +351,44 @@ def stream_scores_host_corpus(pq: PackedQueries, ps: TensorOrList, batch_size: i
     return out
 
 
+def calibrate_pass_costs(device: Union[str, torch.device, None] = None, pages: int = 12_000, page_tokens: int = 1030,
+                         iters: int = 6) -> dict:
+    """Measure, on THIS device, what one pass of every K1 form costs (one CTA per SM with 1..3 resident query tiles, CTA
+    pairs with 2..10) over a synthetic ColPali-shaped store, and install the table in the pass planner
+    (``lis_set_pass_costs``).  The built-in table comes from one power-capped B200; boxes differ by +-10 %.  Takes about a
+    second; returns ``{"single": [...], "pair": [...]}`` in milliseconds."""
+    from .index import LateInteractionIndex
+
+    lib = N.load()
+    dev = resolve_device(device)
+    idx = LateInteractionIndex(pages * page_tokens, pages, device=dev)
+    single, pair = np.zeros(4, np.float32), np.zeros(11, np.float32)
+    try:
+        idx.fill_synthetic(pages, page_tokens, seed=11)
+        store = idx._as_store()
+        g = torch.Generator().manual_seed(1)
+        for form, counts, table in (("single", (1, 2, 3), single), ("pair", tuple(range(2, 11)), pair)):
+            for n in counts:
+                q = torch.nn.functional.normalize(torch.randn(n * 4, 32, N.DIM, generator=g), dim=-1).to(torch.bfloat16).to(dev)
+                pq = pack_queries(q, dev)
+                out = torch.empty((n * 4, pages), dtype=torch.float32, device=dev)
+                N.check(lib.lis_set_tuning(0, n, 0, 0, 1 if form == "single" else 3))
+                for _ in range(3):
+                    maxsim_scores_device(pq, store, "f32", out=out)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    maxsim_scores_device(pq, store, "f32", out=out)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                table[n] = e0.elapsed_time(e1) / iters
+    finally:
+        lib.lis_set_tuning(0, 0, 0, 0, 0)
+        idx.close()
+    N.check(lib.lis_set_pass_costs(single.ctypes.data, pair.ctypes.data))
+    return {"single": single.tolist(), "pair": pair.tolist()}
+
+
 _COPY_STREAMS: dict = {}
 
 

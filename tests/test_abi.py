@@ -117,6 +117,25 @@ def test_new_entry_points_validate_without_gpu(native):
     lib.lis_stream_release()
 
 
+def test_pass_costs_drive_the_planner(native):
+    """lis_set_pass_costs (host-only): the plan follows the installed table; NULL restores the built-in one."""
+    lib = native.load()
+    buf = (C.c_int32 * 64)()
+    plan = lambda n: [buf[i] for i in range(lib.lis_maxsim_pass_plan(n, buf, 64))]
+    default7 = plan(7)
+    assert default7 == [-7]
+    single = np.asarray([0, 1.0, 2.0, 3.0], np.float32)
+    pair = np.asarray([0, 0] + [100.0] * 9, np.float32)          # pairs made expensive: everything runs on single CTAs
+    try:
+        native.check(lib.lis_set_pass_costs(single.ctypes.data, pair.ctypes.data))
+        assert all(x > 0 for x in plan(7)) and sum(plan(7)) == 7
+        bad = np.asarray([0, -1.0, 2.0, 3.0], np.float32)
+        assert lib.lis_set_pass_costs(bad.ctypes.data, None) == native.LIS_E_INVALID
+    finally:
+        native.check(lib.lis_set_pass_costs(None, None))
+    assert plan(7) == default7
+
+
 def test_topk_workspace_sizes(native):
     lib = native.load()
     assert lib.lis_topk_workspace_bytes(1, 100, 10) == 256           # one chunk: no scratch

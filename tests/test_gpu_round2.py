@@ -488,3 +488,20 @@ def test_large_result_is_copied_out_in_blocks_behind_the_kernel(lis, oracle):
     assert torch.equal(ref16, lis.score_multi_vector(qs, pages, return_device=True).cpu())
     with pytest.raises(ValueError, match="out must be"):
         lis.score_multi_vector(qs, pages, out=torch.empty(3, 5))
+
+
+def test_pass_cost_calibration_installs_a_table(lis, oracle):
+    """calibrate_pass_costs measures this device and installs the table; scoring stays correct under it."""
+    N = __import__("importlib").import_module("multi-modal_colpali_b200._native")
+    try:
+        costs = lis.calibrate_pass_costs(pages=1500, iters=2)
+        assert all(c > 0 for c in costs["single"][1:]) and all(c > 0 for c in costs["pair"][2:])
+        assert costs["pair"][10] > costs["pair"][2]
+        g = torch.Generator().manual_seed(111)
+        q = rand_unit(g, 40, 32, 128)                                   # 10 query tiles
+        pages = [rand_unit(g, n, 128) for n in (300, 17, 1030, 64) * 6]
+        want = oracle.score_multi_vector_widened(q, pages)
+        got = lis.score_multi_vector(q, [p.cuda() for p in pages], round_mode="f32")
+        assert (got - want).abs().max().item() <= TOL_F32
+    finally:
+        N.check(N.load().lis_set_pass_costs(None, None))
