@@ -338,7 +338,7 @@ int64_t lis_index_graph_stats(const lis_index* idx, int64_t* captures, int64_t* 
  *                          tensors, as create_document_embeddings returns it), or NULL -- exactly one of the two
  *   p_offsets_host         HOST int64 [np+1] from 0 to n_rows, p_clamp_host HOST uint8 [np] or NULL
  *   out                    device float [n_seg, ld_out]
- *   chunk_rows             token rows per chunk (0 = default, 512 Ki rows = 128 MiB)
+ *   chunk_rows             token rows per chunk (0 = default, 256 Ki rows = 64 MiB)
  *   host_threads           threads gathering pageable rows into the pinned buffer (0 = default)
  * Staging buffers (2 pinned + 2 device chunks) are kept per device between calls; lis_stream_release frees them.
  * Synchronous on return. */

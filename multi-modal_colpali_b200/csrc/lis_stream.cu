@@ -147,8 +147,10 @@ int lis_stream_scores(const void* q, int64_t q_rows, const int32_t* seg_lo, cons
               "lis_stream_scores: offsets must run from 0 to n_rows");
   LIS_REQUIRE(ld_out >= np, "ld_out < np");
   LIS_REQUIRE(chunk_rows >= 0, "chunk_rows < 0");
-  if (chunk_rows == 0) chunk_rows = int64_t(1) << 19;   // 128 MiB of 16-bit rows
-  if (host_threads <= 0) host_threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+  // defaults from profiles/host_corpus_sweep_r2.jsonl: 64 MiB chunks gathered by up to 16 threads (0.85 of the PCIe floor from
+  // pageable memory; 128 MiB / 8 threads: 0.5-0.7)
+  if (chunk_rows == 0) chunk_rows = int64_t(1) << 18;
+  if (host_threads <= 0) host_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
   int64_t max_page = 0;
   for (int64_t p = 0; p < np; ++p) {
     LIS_REQUIRE(p_offsets_host[p + 1] >= p_offsets_host[p], "offsets must be ascending (page %lld)", (long long)p);

@@ -131,3 +131,61 @@ def test_query_batcher_coalesces_and_routes_results(lis):
     with pytest.raises(RuntimeError, match="boom"):
         b.search(torch.zeros(4, 128), 2)
     b.close()
+
+
+def test_query_batcher_keeps_queries_off_the_64_row_cuts(lis):
+    """Bit-identity with one-at-a-time search needs every query to be cut into the same segments as when it is alone:
+    the batcher pads with zero rows so that no query crosses a multiple of 64 packed rows unless it starts on one."""
+    seen = []
+
+    class FakeIndex:
+        dtype = torch.float32
+
+        def search(self, qs, k, round_mode):
+            seen.append([int(q.shape[0]) for q in qs])
+            assert all(float(q.abs().sum()) == 0 for q in qs if q.shape[0] not in (40, 70, 16, 64))   # fillers are zero rows
+            n = len(qs)
+            return torch.arange(n * k, dtype=torch.float32).reshape(n, k), torch.arange(n * k).reshape(n, k)
+
+    b = lis.QueryBatcher(FakeIndex(), max_rows=256, max_wait_ms=200)
+    futs = [b.submit(torch.ones(n, 128), 2) for n in (40, 40, 70, 16, 64)]
+    b.close()
+    [f.result(timeout=10) for f in futs]
+    flat = [n for batch in seen for n in batch]
+    assert [n for n in flat if n in (40, 70, 16, 64)] == [40, 40, 70, 16, 64]          # order of arrival kept
+    for batch in seen:
+        row = 0
+        for n in batch:
+            if n in (40, 70, 16, 64):      # a real query: either it fits before the next cut or it starts on one
+                assert row % 64 == 0 or row % 64 + n <= 64, (batch, row, n)
+            row += n
+        assert row <= 256
+    assert lis.QueryBatcher._placed_rows(40, 40) == 104 and lis.QueryBatcher._placed_rows(64, 70) == 134
+    assert lis.QueryBatcher._placed_rows(10, 54) == 64
+
+
+def test_shard_assignment_and_manifest_errors(lis, tmp_path):
+    assert lis.assign_shards([5, 5, 5, 5], 4) == [(0, 1), (1, 2), (2, 3), (3, 4)]          # one shard per rank
+    parts = lis.assign_shards([10, 10, 10, 10, 10, 10, 10, 10], 2)
+    assert parts == [(0, 4), (4, 8)]
+    parts = lis.assign_shards([100, 1, 1, 1], 2)                                          # balanced by rows, contiguous
+    assert parts[0][0] == 0 and parts[-1][1] == 4 and parts[0][1] == parts[1][0]
+    with pytest.raises(ValueError, match="manifest"):
+        lis.LateInteractionIndex.read_manifest(tmp_path)
+    (tmp_path / "manifest.json").write_text('{"format": "something-else", "dim": 128}')
+    with pytest.raises(ValueError, match="lis-index-v2"):
+        lis.LateInteractionIndex.read_manifest(tmp_path)
+
+
+def test_dataset_fingerprint_sees_in_place_edits():
+    import importlib
+
+    api = importlib.import_module("multi-modal_colpali_b200.reference_api")
+    ds = [{"embedding": torch.zeros(3, 128)} for _ in range(7)]
+    fp = api._dataset_fingerprint(ds)
+    assert api._dataset_fingerprint(ds) == fp
+    ds[3] = {"embedding": torch.zeros(3, 128)}              # same length, another tensor
+    assert api._dataset_fingerprint(ds) != fp
+    fp = api._dataset_fingerprint(ds)
+    ds[3]["embedding"].add_(1)                               # same tensor, edited in place
+    assert api._dataset_fingerprint(ds) != fp
