@@ -281,6 +281,7 @@ static int append_tables(lis_index* ix, const int32_t* lens, int32_t fixed_len, 
 int lis_index_add(lis_index* ix, const void* tokens, const int32_t* lens, const int64_t* ids,
                   const uint8_t* clamp, int64_t n, void* stream) {
   LIS_REQUIRE(ix && lens, "lis_index_add: null pointer");
+  std::lock_guard<std::mutex> lock(ix->mu);      // ingestion and search never overlap on one index
   cudaStream_t st = (cudaStream_t)stream;
   LIS_CUDA_CHECK(cudaSetDevice(ix->device));
   int64_t new_rows = 0;
@@ -292,7 +293,6 @@ int lis_index_add(lis_index* ix, const void* tokens, const int32_t* lens, const 
     if (ix->dtype == LIS_F32X2) {
       // fp32 rows land in the index's own scratch (the search workspace, grown on demand like for a search: no
       // allocation per call), then get split into the planes
-      std::lock_guard<std::mutex> lock(ix->mu);
       int rc1 = ensure(ix, &ix->topk_ws, &ix->topk_ws_bytes, new_rows * 512);
       if (rc1) return rc1;
       float* stage = static_cast<float*>(ix->topk_ws);
