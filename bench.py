@@ -250,7 +250,21 @@ def run_ours(args):
     pages = args.pages
     search_pages = max(args.search_pages, pages)
     rows = pages * PAGE_TOK
-    index = lis.LateInteractionIndex(search_pages * PAGE_TOK, search_pages, device=dev)
+    index = None
+    while index is None:          # 500 000 pages are 131.8 GB: on a GPU with less free memory the search corpus shrinks (and says so)
+        try:
+            index = lis.LateInteractionIndex(search_pages * PAGE_TOK, search_pages, device=dev)
+        except (MemoryError, RuntimeError):
+            if search_pages <= pages:
+                raise
+            search_pages = max(pages, search_pages * 3 // 4)
+    if world > 1:                 # every rank must hold the same number of pages (ids are rank * search_pages + local)
+        t = torch.tensor([search_pages], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if int(t.item()) != search_pages:
+            search_pages = int(t.item())
+            index.close()
+            index = lis.LateInteractionIndex(search_pages * PAGE_TOK, search_pages, device=dev)
     index.fill_synthetic(search_pages, PAGE_TOK, seed=2002 + rank, id_base=rank * search_pages)
     whole = index._as_store()
     store = scoring.PageStore(whole.tokens[:rows], whole.offsets[:pages + 1], whole.clamp[:pages], pages)
