@@ -424,24 +424,31 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const int pe_tile = rel_end(pend);
 
         // Take this set's use `my_use`: all 128 columns of the slot into registers, slot handed back at once.
-        // v3 receives chunk `rot` of the slot, v0..v2 the chunks rot+1, rot+2, rot+3 (mod 4); rot = 3 is the plain order.
-        auto take_use = [&](const uint32_t my_use, const bool split, const uint32_t rot, uint32_t (&v0)[32],
-                            uint32_t (&v1)[32], uint32_t (&v2)[32], uint32_t (&v3)[32]) {
+        // A use is read out in two steps so that at most 96 accumulator values are in registers at once (with all 128
+        // the page cursor no longer fits the 168 registers of a 384-thread CTA, and a spill is an L2 round trip here):
+        // take_a waits for the slot and loads chunks rot+1, rot+2, rot+3 (mod 4) into v0..v2; after the caller has folded
+        // them, take_b loads chunk rot into v3 and hands the slot back.  rot = 3 is the plain order.
+        auto take_a = [&](const uint32_t my_use, const uint32_t rot, uint32_t (&v0)[32], uint32_t (&v1)[32], uint32_t (&v2)[32]) {
           const uint32_t slot = my_use & (NACC - 1);
           const long long ec0 = st_on ? clock64() : 0;
           mbar_wait_u32(acc_full_u + slot * 8, (my_use / NACC) & 1u);
-          const long long ec1 = st_on ? clock64() : 0;
+          if (st_on) st_wait += clock64() - ec0;
           tc_fence_after();
           const uint32_t taddr = tlane + slot * kSlotCols;
           tmem_ld32(taddr + 32u * ((rot + 1u) & 3u), v0);
           tmem_ld32(taddr + 32u * ((rot + 2u) & 3u), v1);
           tmem_ld32(taddr + 32u * ((rot + 3u) & 3u), v2);
-          tmem_ld32(taddr + 32u * rot, v3);
+          tmem_ld_wait();
+        };
+        auto take_b = [&](const uint32_t my_use, const uint32_t rot, uint32_t (&v3)[32]) {
+          const uint32_t slot = my_use & (NACC - 1);
+          const long long hc0 = st_on ? clock64() : 0;
+          tmem_ld32(tlane + slot * kSlotCols + 32u * rot, v3);
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster_u32(acc_empty_l + slot * 8);    // slot back to the MMA warps
-          if (st_on) { st_wait += ec1 - ec0; const long long hc = clock64() - ec1; st_hold += hc; if (split) { st_hold_split += hc; st_wait_split += ec1 - ec0; ++st_n_split; } }
+          if (st_on) st_hold += clock64() - hc0;
         };
 
         const bool live_tile = p < npages;
@@ -460,14 +467,18 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             use_base += split ? 1u : 2u;
             float m = rm[0];
             if (have) {
-              uint32_t v0[32], v1[32], v2[32], v3[32];
-              take_use(my_use, split, 3u, v0, v1, v2, v3);
-              if (live_tile) {
-                m = max32(v0, m);
-                m = max32(v1, m);
-                m = max32(v2, m);
-                m = max32(v3, m);
+              {
+                uint32_t v0[32], v1[32], v2[32];
+                take_a(my_use, 3u, v0, v1, v2);
+                if (live_tile) {
+                  m = max32(v0, m);
+                  m = max32(v1, m);
+                  m = max32(v2, m);
+                }
               }
+              uint32_t v3[32];
+              take_b(my_use, 3u, v3);
+              if (live_tile) m = max32(v3, m);
             }
             rotate(m);
           }
@@ -511,12 +522,17 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 if (b < 0) b = 0;
               } else n_old = 3;
               const uint32_t c = (uint32_t)n_old;
-              uint32_t v0[32], v1[32], v2[32], v3[32];
               const long long q0 = st_on ? clock64() : 0;
-              take_use(my_use, split, c, v0, v1, v2, v3);
+              float f0, f1, f2;
+              {
+                uint32_t v0[32], v1[32], v2[32];
+                take_a(my_use, c, v0, v1, v2);
+                // v0, v1, v2 = chunks c+1, c+2, c+3 (mod 4): behind c -> next page, before c (wrapped around) -> ending page
+                f0 = max32(v0, -INFINITY); f1 = max32(v1, -INFINITY); f2 = max32(v2, -INFINITY);
+              }
+              uint32_t v3[32];
+              take_b(my_use, c, v3);
               const long long q1 = st_on ? clock64() : 0;
-              // v0, v1, v2 = chunks c+1, c+2, c+3 (mod 4): behind c -> next page, before c (wrapped around) -> ending page
-              const float f0 = max32(v0, -INFINITY), f1 = max32(v1, -INFINITY), f2 = max32(v2, -INFINITY);
               const bool n0 = c + 1u < 4u, n1 = c + 2u < 4u, n2 = c + 3u < 4u;
               m_new = fmax3(m_new, n0 ? f0 : -INFINITY, n1 ? f1 : -INFINITY);
               m_new = fmaxf(m_new, n2 ? f2 : -INFINITY);
@@ -609,13 +625,17 @@ maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           }
           use_base += split ? 1u : 2u;
           if (have) {
-            uint32_t v0[32], v1[32], v2[32], v3[32];
-            take_use(my_use, split, 3u, v0, v1, v2, v3);
-            skip_to(cb0);
-            scan(v0, cb0);
-            scan(v1, cb0 + 32);
-            skip_to(cb1);
-            scan(v2, cb1);
+            {
+              uint32_t v0[32], v1[32], v2[32];
+              take_a(my_use, 3u, v0, v1, v2);
+              skip_to(cb0);
+              scan(v0, cb0);
+              scan(v1, cb0 + 32);
+              skip_to(cb1);
+              scan(v2, cb1);
+            }
+            uint32_t v3[32];
+            take_b(my_use, 3u, v3);
             scan(v3, cb1 + 32);
           }
           skip_to(NT);
