@@ -26,7 +26,7 @@ struct Tuning {
   // pass planner: steady-state cost of one pass over a reference store (any unit), by resident query tiles;
   // defaults measured on a power-capped B200 (profiles/pass_costs_r2.jsonl), replaceable with lis_set_pass_costs
   float cost_single[4] = {0.f, 2.65f, 3.90f, 5.40f};
-  float cost_pair[11] = {0.f, 0.f, 4.05f, 5.45f, 6.35f, 8.05f, 8.95f, 10.75f, 11.90f, 14.00f, 14.90f};
+  float cost_pair[11] = {0.f, 0.f, 4.10f, 4.95f, 6.10f, 7.40f, 8.55f, 10.00f, 11.40f, 13.10f, 14.15f};
 };
 extern Tuning g_tuning;
 

@@ -368,8 +368,8 @@ static void build_pass_plan(const Tuning& tn, int64_t n_mtiles, bool must_single
   } else {
     // auto: the cheapest decomposition of n_mtiles by the measured steady-state cost of one pass of each
     // form (ms per 60 000 ColPali pages on a power-capped B200, scripts/gpu_pass_costs.py -> profiles/).
-    // One CTA per SM up to 3 tiles (a single tile is HBM-bound; at 2 and 3 tiles the two forms tie); CTA pairs from 4
-    // tiles on, every count 4..10 in ONE pass (an odd count ends with the full-rate N = 256 use of the split tile);
+    // One CTA per SM for 1 and 2 tiles (a single tile is HBM-bound; at 2 tiles the two forms tie); CTA pairs from 3
+    // tiles on, every count 3..10 in ONE pass (an odd count ends with the full-rate N = 256 use of the split tile);
     // 8 and 10 tiles amortise the page stream a little more.
     const float* cost_single = tn.cost_single;
     const float* cost_pair = tn.cost_pair;     // 0 = shape not available

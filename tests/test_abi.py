@@ -170,9 +170,9 @@ def test_pass_plan_covers_every_tile_once(native, n_tiles):
             assert lib.lis_maxsim_pass_plan(n_tiles, None, 0) == n
     finally:
         lib.lis_set_tuning(0, 0, 0, 0, 0)
-    # auto: one CTA per SM up to 3 tiles, CTA pairs from 4 on
+    # auto: one CTA per SM up to 2 tiles, CTA pairs from 3 on
     n = lib.lis_maxsim_pass_plan(n_tiles, buf, 1024)
-    if n_tiles <= 3:
+    if n_tiles <= 2:
         assert [buf[i] for i in range(n)] == [n_tiles]
-    elif n_tiles in (4, 5, 6, 7, 8, 9, 10):
+    elif n_tiles in (3, 4, 5, 6, 7, 8, 9, 10):
         assert [buf[i] for i in range(n)] == [-n_tiles]
