@@ -189,3 +189,23 @@ def test_dataset_fingerprint_sees_in_place_edits():
     fp = api._dataset_fingerprint(ds)
     ds[3]["embedding"].add_(1)                               # same tensor, edited in place
     assert api._dataset_fingerprint(ds) != fp
+
+
+def test_product_never_imports_the_oracle_and_has_no_cpu_path():
+    """The oracle is test infrastructure: nothing under the product package may import or execute it, and bench.py's own
+    arm refuses to run without a GPU instead of falling back."""
+    import re
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    for f in (root / "multi-modal_colpali_b200").rglob("*.py"):
+        text = f.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+        assert "maxsim_oracle" not in text, f
+    for f in (root / "multi-modal_colpali_b200" / "csrc").glob("*"):
+        assert "oracle" not in f.read_text().lower(), f
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, str(root / "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
+        assert r.returncode != 0 and "no CPU path" in (r.stderr + r.stdout)
