@@ -139,7 +139,7 @@ int lis_reduce_segments(const float* seg_scores, int64_t ld_seg, const int32_t* 
  *   a_operand  {0, 1, 2, 3}        query operand of the MMA in shared memory (1) or tensor memory (2) on one
  *                                  CTA per SM, or 3 = CTA pairs (clusters of 2, tcgen05 cta_group::2: every page
  *                                  tile is loaded once per pair and shared by up to 10 query tiles).  Auto: the cheapest
- *                                  mix of passes by measured cost (one CTA per SM up to 3 tiles, pairs from 4). */
+ *                                  mix of passes by measured cost (one CTA per SM for 1-2 tiles, pairs from 3; see lis_set_pass_costs). */
 int lis_set_tuning(int tile_n, int group, int max_ctas, int epi_halves, int a_operand);
 /* The pass planner picks, for a batch of n query tiles, the cheapest mix of passes by the cost of one pass of every form
  * (single[1..3]: one CTA per SM with 1..3 resident tiles; pair[2..10]: CTA pairs with 2..10), in any common unit.  The
