@@ -415,12 +415,12 @@ class LateInteractionIndex:
         plan = plan_queries(lens)
         if plan.n_seg == 0:
             raise ValueError("No queries provided")
-        out_s = torch.empty((plan.nq, k), dtype=torch.float32)
-        out_i = torch.empty((plan.nq, k), dtype=torch.int64)
+        out_s = torch.empty(plan.nq, k, dtype=torch.float32)
+        out_i = torch.empty(plan.nq, k, dtype=torch.int64)
         # (the C call selects the index's device itself; no torch device guard on this latency path)
+        seg_lo, seg_hi, mt_seg, seg_first = plan.host_ptrs
         N.check(self._lib.lis_index_search_sharded(
-            self._h, comm, rows.data_ptr(), rows.shape[0], plan.seg_lo.ctypes.data, plan.seg_hi.ctypes.data,
-            plan.mt_seg.ctypes.data, plan.n_seg, plan.n_mtiles, None if plan.direct else plan.seg_first.ctypes.data,
+            self._h, comm, rows.data_ptr(), plan.n_rows, seg_lo, seg_hi, mt_seg, plan.n_seg, plan.n_mtiles, seg_first,
             plan.nq, _ROUND[round_mode], k, out_s.data_ptr(), out_i.data_ptr(),
             torch.cuda.current_stream(rows.device).cuda_stream if rows.is_cuda else None))
         return out_s, out_i
@@ -456,22 +456,31 @@ class LateInteractionIndex:
 
 def _flatten_queries(qs: TensorOrList, dtype: torch.dtype) -> Tuple[torch.Tensor, Tuple[int, ...]]:
     """Queries as ONE contiguous ``[rows, 128]`` matrix of the index dtype, where they already live (host
-    tensors stay on the host: the C call uploads them together with the segment tables), plus their lengths."""
+    tensors stay on the host: the C call uploads them together with the segment tables), plus their lengths.
+    This sits on the latency path of a small-corpus search, hence the early exits for data that is already in shape."""
     if isinstance(qs, torch.Tensor) and qs.dim() == 3:
         nq, n_tok, d = qs.shape
         if d != N.DIM:
             raise ValueError(f"queries: embedding width {d} != {N.DIM}")
-        flat, lens = qs.reshape(nq * n_tok, d), (n_tok,) * nq
+        lens = (n_tok,) * nq
+        if qs.dtype == dtype and qs.is_contiguous():
+            return qs.detach().view(nq * n_tok, d), lens
+        flat = qs.reshape(nq * n_tok, d)
     else:
-        ql = _as_list(qs)
+        ql = qs if isinstance(qs, (list, tuple)) else _as_list(qs)
+        if len(ql) == 0:
+            raise ValueError("No queries provided")
+        dev, same_dev = ql[0].device, True
         for t in ql:
             _check_rows(t, "query")
-        lens = tuple(int(t.shape[0]) for t in ql)
-        if len({t.device for t in ql}) > 1:
+            same_dev = same_dev and t.device == dev
+        lens = tuple(t.shape[0] for t in ql)
+        if not same_dev:
             ql = [t.cpu() for t in ql]
         flat = ql[0] if len(ql) == 1 else torch.cat(ql, dim=0)
-    flat = flat.detach().to(dtype).contiguous()
-    return flat, lens
+        if flat.dtype == dtype and flat.is_contiguous():
+            return flat.detach(), lens
+    return flat.detach().to(dtype).contiguous(), lens
 
 
 class _CudaArrayView:

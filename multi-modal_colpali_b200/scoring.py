@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass
-from functools import lru_cache
+from functools import cached_property, lru_cache
 from typing import List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -60,16 +60,25 @@ class QueryPlan:
     mt_seg: np.ndarray      # int32 [n_mtiles+1]
     seg_first: np.ndarray   # int32 [nq+1]  segments of query q = seg_first[q]..seg_first[q+1]
 
-    @property
+    @cached_property
     def direct(self) -> bool:
         """True when K1's output rows are the per-query scores: segment s belongs to query s, i.e. no query was
         cut and none is empty (an empty query owns no segment, so the counts alone cannot tell: lens [0, 100] give
         two segments of query 1)."""
         return self.n_seg == self.nq and bool((self.seg_query == np.arange(self.nq, dtype=np.int32)).all())
 
+    @cached_property
+    def host_ptrs(self) -> Tuple[int, int, int, Optional[int]]:
+        """Host addresses of (seg_lo, seg_hi, mt_seg, seg_first or None when ``direct``) -- what the one-shot search
+        passes to the C call.  Plans are cached and immutable, so the addresses are computed once per query shape."""
+        return (self.seg_lo.ctypes.data, self.seg_hi.ctypes.data, self.mt_seg.ctypes.data,
+                None if self.direct else self.seg_first.ctypes.data)
+
 
 def plan_queries(q_lens: Sequence[int]) -> QueryPlan:
-    return _plan_cached(tuple(int(x) for x in q_lens))
+    if type(q_lens) is not tuple:
+        q_lens = tuple(int(x) for x in q_lens)
+    return _plan_cached(q_lens)
 
 
 @lru_cache(maxsize=256)

@@ -209,3 +209,42 @@ def test_product_never_imports_the_oracle_and_has_no_cpu_path():
     if not torch.cuda.is_available():
         r = subprocess.run([sys.executable, str(root / "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
         assert r.returncode != 0 and "no CPU path" in (r.stderr + r.stdout)
+
+
+def test_flatten_queries_fast_and_slow_paths_agree():
+    """The one-shot search packs queries on the host; data already in shape must pass through untouched
+    (no copy), everything else must come out as ONE contiguous [rows, 128] matrix of the index dtype."""
+    import importlib
+
+    index = importlib.import_module("multi-modal_colpali_b200.index")
+    scoring = importlib.import_module("multi-modal_colpali_b200.scoring")
+    g = torch.Generator().manual_seed(5)
+    q3 = torch.randn(4, 20, 128, generator=g).to(torch.bfloat16)
+    flat, lens = index._flatten_queries(q3, torch.bfloat16)
+    assert lens == (20,) * 4 and flat.shape == (80, 128) and flat.data_ptr() == q3.data_ptr()      # aliased, not copied
+    flat32, _ = index._flatten_queries(q3.float(), torch.bfloat16)                                # dtype conversion
+    assert flat32.dtype == torch.bfloat16 and torch.equal(flat32, flat)
+    strided = torch.randn(4, 40, 128, generator=g).to(torch.bfloat16)[:, ::2]                     # not contiguous
+    flat_s, lens_s = index._flatten_queries(strided, torch.bfloat16)
+    assert flat_s.is_contiguous() and lens_s == (20,) * 4 and torch.equal(flat_s, strided.reshape(80, 128))
+    ragged = [q3[0], q3[1][:7], torch.empty(0, 128, dtype=torch.bfloat16), q3[2][3:]]
+    flat_r, lens_r = index._flatten_queries(ragged, torch.bfloat16)
+    assert lens_r == (20, 7, 0, 17) and torch.equal(flat_r, torch.cat(ragged))
+    one, lens_1 = index._flatten_queries([q3[3]], torch.bfloat16)
+    assert lens_1 == (20,) and one.data_ptr() == q3[3].data_ptr()
+    assert index._flatten_queries(tuple(ragged), torch.float16)[0].dtype == torch.float16
+    assert index._flatten_queries((t for t in ragged), torch.bfloat16)[1] == lens_r               # any iterable
+    with pytest.raises(ValueError):
+        index._flatten_queries(torch.zeros(2, 5, 64), torch.bfloat16)
+    with pytest.raises(ValueError):
+        index._flatten_queries([torch.zeros(5, 64)], torch.bfloat16)
+    with pytest.raises(ValueError):
+        index._flatten_queries(torch.zeros(5, 128), torch.bfloat16)                                # one query needs a list
+    # the plan carries the host addresses the C call receives; seg_first only when K1's rows are not the queries
+    for lens in [(20,) * 4, (20,) * 10, (0, 100), (7,), (64, 64), (130,)]:
+        plan = scoring.plan_queries(lens)
+        lo, hi, mt, first = plan.host_ptrs
+        assert (lo, hi, mt) == (plan.seg_lo.ctypes.data, plan.seg_hi.ctypes.data, plan.mt_seg.ctypes.data)
+        assert (first is None) == plan.direct and (plan.direct or first == plan.seg_first.ctypes.data)
+        assert plan.n_rows == sum(lens)
+        assert scoring.plan_queries(list(lens)) is plan and scoring.plan_queries(np.asarray(lens)) is plan
